@@ -1,0 +1,843 @@
+// vkrt_api.cu -- context, scene upload and the render loop behind the C ABI
+// (include/vkrt_b200.h).  Host-side orchestration only: every pixel of work is done
+// by the kernels in vkrt_bvh.cu / vkrt_trace.cu / vkrt_shade.cu.
+//
+// Reference counterparts: Renderer::setup/create/run/destroy (src/renderer.h:30-48),
+// RayQuery::run (src/rayquery.cpp:96-109), Scene::load upload half (src/scene.cpp:93-109),
+// AccelStructure::create (src/accelstruct.cpp:55-65), RenderOutput (src/render_output.cpp:78-182).
+#include <vector>
+#include <string>
+#include <cstring>
+#include <cstdio>
+#include <algorithm>
+#include "vkrt_device.cuh"
+#include "vkrt_internal.h"
+
+using namespace vkrt;
+
+namespace vkrt {
+void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats);
+}
+
+struct HostMesh
+{
+  std::vector<VertexAttributes> vtx;
+  std::vector<uint32_t>         idx;
+  int32_t                       material;
+};
+struct HostNode
+{
+  float    world[16];
+  uint32_t mesh;
+};
+struct HostTexture
+{
+  std::vector<uint8_t> rgba;
+  uint32_t             w, h;
+  int32_t              linear, wrapS, wrapT;
+};
+
+enum TimerSlot { T_RAYGEN = 0, T_CLOSEST, T_SHADOW, T_SHADE, T_SORT, T_ACCUM, T_TONEMAP, T_COUNT };
+
+struct vkrt_ctx
+{
+  int          device = 0;
+  cudaStream_t stream = nullptr;
+  int          numSMs = 148;
+  std::string  err;
+
+  // host staging (between scene_begin and scene_commit)
+  std::vector<HostMesh>          meshes;
+  std::vector<HostNode>          nodes;
+  std::vector<GltfShadeMaterial> materials;
+  std::vector<Light>             lights;
+  std::vector<HostTexture>       textures;
+
+  // device scene
+  VertexAttributes*    dVerts = nullptr;
+  uint32_t*            dIdx = nullptr;
+  InstanceData*        dGeo = nullptr;
+  InstanceXform*       dInst = nullptr;
+  uint32_t*            dInstTriOffset = nullptr;
+  GltfShadeMaterial*   dMat = nullptr;
+  Light*               dLights = nullptr;
+  TexDesc*             dTexDescs = nullptr;
+  std::vector<uchar4*> dTexData;
+  float4*              dEnv = nullptr;
+  EnvAccel*            dEnvAccel = nullptr;
+  BvhResult            bvh;
+  SceneView            view{};
+  bool                 committed = false;
+  bool                 hasEnv = false;
+
+  // output image
+  float4* image = nullptr;
+  bool    ownsImage = false;
+  int     W = 0, H = 0;
+  float4* dToneF = nullptr;
+  uchar4* dTone8 = nullptr;
+
+  // wavefront
+  Wavefront wf{};
+  size_t    wfCapacity = 0;   // paths
+  uint32_t* dPixelOfLocal = nullptr;
+  size_t    pixCapacity = 0;
+  int       shardKey[5] = {-1, -1, -1, -1, -1};  // W,H,tile,rank,count
+
+  // stats
+  TraceStats* dStats = nullptr;
+  vkrt_stats  stats{};
+  struct Timed { cudaEvent_t a, b; int slot; };
+  std::vector<Timed>       pending;
+  std::vector<cudaEvent_t> eventPool;
+};
+
+#define CTX_CHECK(call)                                                                                                \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t e_ = (call);                                                                                           \
+    if(e_ != cudaSuccess)                                                                                              \
+    {                                                                                                                  \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                                   \
+      return VKRT_ERR_CUDA;                                                                                            \
+    }                                                                                                                  \
+  } while(0)
+
+static int fail(vkrt_ctx* ctx, int code, const char* msg)
+{
+  if(ctx)
+    ctx->err = msg;
+  return code;
+}
+
+static void freeScene(vkrt_ctx* c)
+{
+  cudaFree(c->dVerts); cudaFree(c->dIdx); cudaFree(c->dGeo); cudaFree(c->dInst); cudaFree(c->dInstTriOffset);
+  cudaFree(c->dMat); cudaFree(c->dLights); cudaFree(c->dTexDescs);
+  for(auto p : c->dTexData) cudaFree(p);
+  c->dTexData.clear();
+  cudaFree(c->bvh.nodes); cudaFree(c->bvh.tris); cudaFree(c->bvh.triInfo);
+  c->dVerts = nullptr; c->dIdx = nullptr; c->dGeo = nullptr; c->dInst = nullptr; c->dInstTriOffset = nullptr;
+  c->dMat = nullptr; c->dLights = nullptr; c->dTexDescs = nullptr;
+  c->bvh = BvhResult{};
+  c->committed = false;
+}
+
+static void freeWavefront(vkrt_ctx* c)
+{
+  Wavefront& w = c->wf;
+  cudaFree(w.rayO); cudaFree(w.rayD); cudaFree(w.hit); cudaFree(w.thr); cudaFree(w.rad); cudaFree(w.absb); cudaFree(w.sum);
+  cudaFree(w.shO); cudaFree(w.shD); cudaFree(w.shC); cudaFree(w.queueCur); cudaFree(w.queueNext); cudaFree(w.counters);
+  w = Wavefront{};
+  c->wfCapacity = 0;
+}
+
+static cudaEvent_t getEvent(vkrt_ctx* c)
+{
+  if(!c->eventPool.empty())
+  {
+    cudaEvent_t e = c->eventPool.back();
+    c->eventPool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+static void drainTimers(vkrt_ctx* c)
+{
+  if(c->pending.empty())
+    return;
+  cudaStreamSynchronize(c->stream);
+  double acc[T_COUNT] = {0};
+  for(auto& t : c->pending)
+  {
+    float ms = 0.f;
+    if(cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess)
+      acc[t.slot] += ms;
+    c->eventPool.push_back(t.a);
+    c->eventPool.push_back(t.b);
+  }
+  c->pending.clear();
+  c->stats.ms_raygen += acc[T_RAYGEN];
+  c->stats.ms_trace_closest += acc[T_CLOSEST];
+  c->stats.ms_trace_shadow += acc[T_SHADOW];
+  c->stats.ms_shade += acc[T_SHADE];
+  c->stats.ms_sort += acc[T_SORT];
+  c->stats.ms_accumulate += acc[T_ACCUM];
+  c->stats.ms_tonemap += acc[T_TONEMAP];
+}
+
+struct ScopedTimer
+{
+  vkrt_ctx*   c;
+  bool        on;
+  cudaEvent_t a{}, b{};
+  int         slot;
+  ScopedTimer(vkrt_ctx* ctx, bool enable, int s) : c(ctx), on(enable), slot(s)
+  {
+    if(on)
+    {
+      a = getEvent(c);
+      b = getEvent(c);
+      cudaEventRecord(a, c->stream);
+    }
+  }
+  ~ScopedTimer()
+  {
+    if(on)
+    {
+      cudaEventRecord(b, c->stream);
+      c->pending.push_back({a, b, slot});
+    }
+  }
+};
+
+extern "C" {
+
+const char* vkrt_name(void) { return "B200 wavefront path tracer (CUDA sm_100a)"; }
+
+const char* vkrt_last_error(vkrt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int vkrt_create(int cuda_device, vkrt_ctx** out_ctx)
+{
+  if(!out_ctx)
+    return VKRT_ERR_INVALID;
+  *out_ctx = nullptr;
+  int n = 0;
+  if(cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+    return VKRT_ERR_CUDA;  // no silent CPU fallback: the product path needs a GPU
+  if(cuda_device < 0 || cuda_device >= n)
+    return VKRT_ERR_INVALID;
+  vkrt_ctx* ctx = new vkrt_ctx();
+  ctx->device   = cuda_device;
+  if(cudaSetDevice(cuda_device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+  {
+    delete ctx;
+    return VKRT_ERR_CUDA;
+  }
+  cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, cuda_device);
+  if(cudaMalloc(&ctx->dStats, sizeof(TraceStats)) != cudaSuccess)
+  {
+    delete ctx;
+    return VKRT_ERR_NOMEM;
+  }
+  cudaMemset(ctx->dStats, 0, sizeof(TraceStats));
+  // default sun & sky: src/sample_example.hpp:176-193 (in_use = 0)
+  SunAndSky ss{};
+  ss.rgb_unit_conversion[0] = ss.rgb_unit_conversion[1] = ss.rgb_unit_conversion[2] = 1.f;
+  ss.multiplier = 0.0000101320f; ss.saturation = 1.0f;
+  ss.ground_color[0] = ss.ground_color[1] = ss.ground_color[2] = 0.4f;
+  ss.horizon_blur = 0.1f; ss.night_color[2] = 0.01f; ss.sun_disk_intensity = 0.8f;
+  ss.sun_direction[1] = 0.78f; ss.sun_direction[2] = 0.62f; ss.sun_disk_scale = 5.0f; ss.sun_glow_intensity = 1.0f;
+  ss.y_is_up = 1; ss.physically_scaled_sun = 1; ss.in_use = 0;
+  ctx->view.sunsky = ss;
+  *out_ctx = ctx;
+  return VKRT_OK;
+}
+
+int vkrt_destroy(vkrt_ctx* ctx)
+{
+  if(!ctx)
+    return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  drainTimers(ctx);
+  for(auto e : ctx->eventPool) cudaEventDestroy(e);
+  freeScene(ctx);
+  freeWavefront(ctx);
+  cudaFree(ctx->dEnv); cudaFree(ctx->dEnvAccel);
+  cudaFree(ctx->dPixelOfLocal);
+  if(ctx->ownsImage) cudaFree(ctx->image);
+  cudaFree(ctx->dToneF); cudaFree(ctx->dTone8);
+  cudaFree(ctx->dStats);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return VKRT_OK;
+}
+
+// ---- scene -------------------------------------------------------------------------------------
+int vkrt_scene_begin(vkrt_ctx* ctx)
+{
+  if(!ctx) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  freeScene(ctx);
+  ctx->meshes.clear(); ctx->nodes.clear(); ctx->materials.clear(); ctx->lights.clear(); ctx->textures.clear();
+  return VKRT_OK;
+}
+
+int vkrt_scene_add_primmesh(vkrt_ctx* ctx, const VertexAttributes* vertices, uint32_t num_vertices, const uint32_t* indices,
+                            uint32_t num_indices, int32_t material_index)
+{
+  if(!ctx) return VKRT_ERR_INVALID;
+  if((!vertices && num_vertices) || (!indices && num_indices) || (num_indices % 3) != 0)
+    return fail(ctx, VKRT_ERR_INVALID, "add_primmesh: bad arrays (indices must be triangle triples)");
+  for(uint32_t i = 0; i < num_indices; i++)
+    if(indices[i] >= num_vertices)
+      return fail(ctx, VKRT_ERR_INVALID, "add_primmesh: index out of range");
+  HostMesh m;
+  m.vtx.assign(vertices, vertices + num_vertices);
+  m.idx.assign(indices, indices + num_indices);
+  m.material = material_index;
+  ctx->meshes.push_back(std::move(m));
+  return VKRT_OK;
+}
+
+int vkrt_scene_add_node(vkrt_ctx* ctx, const float world_matrix[16], uint32_t prim_mesh)
+{
+  if(!ctx || !world_matrix) return VKRT_ERR_INVALID;
+  if(prim_mesh >= ctx->meshes.size())
+    return fail(ctx, VKRT_ERR_INVALID, "add_node: unknown primMesh");
+  HostNode n;
+  std::memcpy(n.world, world_matrix, 64);
+  n.mesh = prim_mesh;
+  ctx->nodes.push_back(n);
+  return VKRT_OK;
+}
+
+int vkrt_scene_set_materials(vkrt_ctx* ctx, const GltfShadeMaterial* materials, uint32_t count)
+{
+  if(!ctx || (!materials && count)) return VKRT_ERR_INVALID;
+  ctx->materials.assign(materials, materials + count);
+  return VKRT_OK;
+}
+
+int vkrt_scene_set_lights(vkrt_ctx* ctx, const Light* lights, uint32_t count)
+{
+  if(!ctx || (!lights && count)) return VKRT_ERR_INVALID;
+  ctx->lights.assign(lights, lights + count);
+  return VKRT_OK;
+}
+
+int vkrt_scene_add_texture(vkrt_ctx* ctx, const uint8_t* rgba8, uint32_t width, uint32_t height, int32_t mag_filter, int32_t min_filter,
+                           int32_t wrap_s, int32_t wrap_t)
+{
+  (void)min_filter;  // LOD 0 sampling always magnifies; mip chains are never generated (src/scene.cpp:540-542)
+  if(!ctx || !rgba8 || width == 0 || height == 0) return VKRT_ERR_INVALID;
+  HostTexture t;
+  t.rgba.assign(rgba8, rgba8 + (size_t)width * height * 4);
+  t.w = width; t.h = height;
+  // src/scene.cpp:451-457: only the LINEAR family maps to VK_FILTER_LINEAR; unknown codes default to NEAREST
+  t.linear = (mag_filter == 9729 || mag_filter == 9985 || mag_filter == 9987) ? 1 : 0;
+  auto wrap = [](int32_t m) { return m == 33071 ? 1 : (m == 33648 ? 2 : 0); };  // src/scene.cpp:467-470, default REPEAT
+  t.wrapS = wrap(wrap_s);
+  t.wrapT = wrap(wrap_t);
+  ctx->textures.push_back(std::move(t));
+  return VKRT_OK;
+}
+
+int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
+{
+  if(!ctx) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if(ctx->materials.empty())
+    return fail(ctx, VKRT_ERR_STATE, "scene_commit: no materials (the importer always appends a default one)");
+  for(auto& m : ctx->meshes)
+    if(m.material >= (int32_t)ctx->materials.size())
+      return fail(ctx, VKRT_ERR_INVALID, "scene_commit: material index out of range");
+  for(auto& m : ctx->materials)
+  {
+    const int32_t ids[] = {m.pbrBaseColorTexture, m.pbrMetallicRoughnessTexture, m.emissiveTexture, m.normalTexture,
+                           m.transmissionTexture, m.clearcoatTexture, m.clearcoatRoughnessTexture};
+    for(int32_t id : ids)
+      if(id >= (int32_t)ctx->textures.size())
+        return fail(ctx, VKRT_ERR_INVALID, "scene_commit: texture index out of range");
+  }
+  freeScene(ctx);
+  cudaEvent_t e0 = getEvent(ctx), e1 = getEvent(ctx);
+  cudaEventRecord(e0, ctx->stream);
+
+  // geometry: one vertex and one index arena, InstanceData per primMesh (src/scene.cpp:161-176)
+  size_t nv = 0, ni = 0;
+  for(auto& m : ctx->meshes) { nv += m.vtx.size(); ni += m.idx.size(); }
+  CTX_CHECK(cudaMalloc(&ctx->dVerts, sizeof(VertexAttributes) * std::max<size_t>(nv, 1)));
+  CTX_CHECK(cudaMalloc(&ctx->dIdx, sizeof(uint32_t) * std::max<size_t>(ni, 1)));
+  std::vector<InstanceData> geo(ctx->meshes.size());
+  {
+    size_t ov = 0, oi = 0;
+    for(size_t i = 0; i < ctx->meshes.size(); i++)
+    {
+      auto& m = ctx->meshes[i];
+      if(!m.vtx.empty())
+        CTX_CHECK(cudaMemcpyAsync(ctx->dVerts + ov, m.vtx.data(), sizeof(VertexAttributes) * m.vtx.size(), cudaMemcpyHostToDevice, ctx->stream));
+      if(!m.idx.empty())
+        CTX_CHECK(cudaMemcpyAsync(ctx->dIdx + oi, m.idx.data(), 4 * m.idx.size(), cudaMemcpyHostToDevice, ctx->stream));
+      geo[i].vertexAddress = (uint64_t)(uintptr_t)(ctx->dVerts + ov);
+      geo[i].indexAddress  = (uint64_t)(uintptr_t)(ctx->dIdx + oi);
+      geo[i].materialIndex = m.material;
+      geo[i]._pad          = 0;
+      ov += m.vtx.size();
+      oi += m.idx.size();
+    }
+  }
+  CTX_CHECK(cudaMalloc(&ctx->dGeo, sizeof(InstanceData) * std::max<size_t>(geo.size(), 1)));
+  if(!geo.empty())
+    CTX_CHECK(cudaMemcpyAsync(ctx->dGeo, geo.data(), sizeof(InstanceData) * geo.size(), cudaMemcpyHostToDevice, ctx->stream));
+
+  // instances: flags per src/accelstruct.cpp:139-149
+  std::vector<InstanceXform> inst(ctx->nodes.size());
+  std::vector<uint32_t>      triOff(ctx->nodes.size() + 1);
+  uint64_t                   totalTris = 0;
+  bool                       nonOpaque = false;
+  for(size_t i = 0; i < ctx->nodes.size(); i++)
+  {
+    const HostNode&          n   = ctx->nodes[i];
+    const HostMesh&          m   = ctx->meshes[n.mesh];
+    const GltfShadeMaterial& mat = ctx->materials[std::max(0, m.material)];
+    uint32_t                 fl  = 0;
+    if(mat.alphaMode == 0 || (mat.pbrBaseColorFactor[3] == 1.0f && mat.pbrBaseColorTexture == -1))
+      fl |= TRI_OPAQUE;
+    if(mat.doubleSided == 1)
+      fl |= TRI_CULL_DISABLE;
+    const float* w = n.world;
+    float det = w[0] * (w[5] * w[10] - w[9] * w[6]) - w[4] * (w[1] * w[10] - w[9] * w[2]) + w[8] * (w[1] * w[6] - w[5] * w[2]);
+    if(det < 0.0f)
+      fl |= TRI_FLIP_FACING;  // Vulkan decides facing in object space
+    if(!(fl & TRI_OPAQUE))
+      nonOpaque = true;
+    float inv[16];
+    if(!invertAffine(w, inv))
+      return fail(ctx, VKRT_ERR_INVALID, "scene_commit: singular node matrix");
+    InstanceXform& I = inst[i];
+    for(int r = 0; r < 3; r++)
+      for(int c = 0; c < 4; c++)
+      {
+        I.o2w[r * 4 + c] = w[c * 4 + r];
+        I.w2o[r * 4 + c] = inv[c * 4 + r];
+      }
+    I.primMesh  = n.mesh;
+    I.flags     = fl;
+    I.triOffset = (uint32_t)totalTris;
+    I.triCount  = (uint32_t)(m.idx.size() / 3);
+    triOff[i]   = (uint32_t)totalTris;
+    totalTris += m.idx.size() / 3;
+  }
+  triOff[ctx->nodes.size()] = (uint32_t)totalTris;
+  if(totalTris > (uint64_t)kLeafMask)
+    return fail(ctx, VKRT_ERR_INVALID, "scene_commit: more than 2^28 triangles after flattening");
+  CTX_CHECK(cudaMalloc(&ctx->dInst, sizeof(InstanceXform) * std::max<size_t>(inst.size(), 1)));
+  CTX_CHECK(cudaMalloc(&ctx->dInstTriOffset, 4 * triOff.size()));
+  if(!inst.empty())
+    CTX_CHECK(cudaMemcpyAsync(ctx->dInst, inst.data(), sizeof(InstanceXform) * inst.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CTX_CHECK(cudaMemcpyAsync(ctx->dInstTriOffset, triOff.data(), 4 * triOff.size(), cudaMemcpyHostToDevice, ctx->stream));
+
+  // materials, lights (never empty: src/scene.cpp:329-330), textures
+  CTX_CHECK(cudaMalloc(&ctx->dMat, sizeof(GltfShadeMaterial) * ctx->materials.size()));
+  CTX_CHECK(cudaMemcpyAsync(ctx->dMat, ctx->materials.data(), sizeof(GltfShadeMaterial) * ctx->materials.size(), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<Light> lights = ctx->lights;
+  if(lights.empty())
+    lights.push_back(Light{});
+  CTX_CHECK(cudaMalloc(&ctx->dLights, sizeof(Light) * lights.size()));
+  CTX_CHECK(cudaMemcpyAsync(ctx->dLights, lights.data(), sizeof(Light) * lights.size(), cudaMemcpyHostToDevice, ctx->stream));
+  std::vector<TexDesc> descs(ctx->textures.size());
+  for(size_t i = 0; i < ctx->textures.size(); i++)
+  {
+    const HostTexture& t = ctx->textures[i];
+    uchar4*            d = nullptr;
+    CTX_CHECK(cudaMalloc(&d, t.rgba.size()));
+    ctx->dTexData.push_back(d);
+    CTX_CHECK(cudaMemcpyAsync(d, t.rgba.data(), t.rgba.size(), cudaMemcpyHostToDevice, ctx->stream));
+    descs[i] = TexDesc{d, (int32_t)t.w, (int32_t)t.h, t.linear, t.wrapS, t.wrapT, 0};
+  }
+  CTX_CHECK(cudaMalloc(&ctx->dTexDescs, sizeof(TexDesc) * std::max<size_t>(descs.size(), 1)));
+  if(!descs.empty())
+    CTX_CHECK(cudaMemcpyAsync(ctx->dTexDescs, descs.data(), sizeof(TexDesc) * descs.size(), cudaMemcpyHostToDevice, ctx->stream));
+
+  // acceleration structure
+  std::string berr;
+  uint64_t    launches = 0;
+  if(!buildBvh(ctx->stream, ctx->dInst, ctx->dInstTriOffset, (uint32_t)inst.size(), ctx->dGeo, (uint32_t)totalTris, build_mode, ctx->bvh, berr, &launches))
+  {
+    ctx->err = "scene_commit: BVH build failed: " + berr;
+    return VKRT_ERR_CUDA;
+  }
+  ctx->stats.kernel_launches += launches;
+  cudaEventRecord(e1, ctx->stream);
+  CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  ctx->eventPool.push_back(e0);
+  ctx->eventPool.push_back(e1);
+  ctx->stats.ms_build       = ms;
+  ctx->stats.num_triangles  = (uint32_t)totalTris;
+  ctx->stats.num_bvh_nodes  = ctx->bvh.numNodes;
+  ctx->stats.num_instances  = (uint32_t)inst.size();
+  ctx->stats.has_non_opaque = nonOpaque ? 1u : 0u;
+
+  SceneView& v   = ctx->view;
+  v.nodes        = ctx->bvh.nodes;
+  v.tris         = ctx->bvh.tris;
+  v.triInfo      = ctx->bvh.triInfo;
+  v.instances    = ctx->dInst;
+  v.geoInfo      = ctx->dGeo;
+  v.materials    = ctx->dMat;
+  v.lights       = ctx->dLights;
+  v.textures     = ctx->dTexDescs;
+  v.numTris      = (uint32_t)totalTris;
+  v.hasNonOpaque = nonOpaque ? 1u : 0u;
+  ctx->committed = true;
+  return VKRT_OK;
+}
+
+// ---- environment / camera --------------------------------------------------------------------------
+int vkrt_build_env_accel(const float* rgba32f, uint32_t width, uint32_t height, EnvAccel* out_accel, float* out_integral, float* out_average)
+{
+  if(!rgba32f || !out_accel || width == 0 || height == 0)
+    return VKRT_ERR_INVALID;
+  buildEnvAccelHost(rgba32f, width, height, out_accel, out_integral, out_average);
+  return VKRT_OK;
+}
+
+int vkrt_set_environment(vkrt_ctx* ctx, const float* rgba32f, uint32_t width, uint32_t height, const EnvAccel* accel)
+{
+  if(!ctx || !rgba32f || width == 0 || height == 0) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->dEnv); cudaFree(ctx->dEnvAccel);
+  ctx->dEnv = nullptr; ctx->dEnvAccel = nullptr;
+  const size_t n = (size_t)width * height;
+  std::vector<EnvAccel> tmp;
+  if(!accel)
+  {
+    tmp.resize(n);
+    buildEnvAccelHost(rgba32f, width, height, tmp.data(), nullptr, nullptr);
+    accel = tmp.data();
+  }
+  CTX_CHECK(cudaMalloc(&ctx->dEnv, n * sizeof(float4)));
+  CTX_CHECK(cudaMalloc(&ctx->dEnvAccel, n * sizeof(EnvAccel)));
+  CTX_CHECK(cudaMemcpyAsync(ctx->dEnv, rgba32f, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+  CTX_CHECK(cudaMemcpyAsync(ctx->dEnvAccel, accel, n * sizeof(EnvAccel), cudaMemcpyHostToDevice, ctx->stream));
+  CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->view.envPixels = ctx->dEnv;
+  ctx->view.envAccel  = ctx->dEnvAccel;
+  ctx->view.envW      = (int32_t)width;
+  ctx->view.envH      = (int32_t)height;
+  ctx->hasEnv         = true;
+  return VKRT_OK;
+}
+
+int vkrt_set_sunsky(vkrt_ctx* ctx, const SunAndSky* s)
+{
+  if(!ctx || !s) return VKRT_ERR_INVALID;
+  ctx->view.sunsky = *s;
+  return VKRT_OK;
+}
+
+int vkrt_set_camera(vkrt_ctx* ctx, const SceneCamera* cam)
+{
+  if(!ctx || !cam) return VKRT_ERR_INVALID;
+  ctx->view.camera = *cam;  // travels as a kernel parameter (the reference's UBO, src/scene.cpp:655)
+  return VKRT_OK;
+}
+
+// ---- output ------------------------------------------------------------------------------------------
+int vkrt_output_create(vkrt_ctx* ctx, uint32_t width, uint32_t height, void* device_rgba32f)
+{
+  if(!ctx || width == 0 || height == 0) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if(ctx->ownsImage) cudaFree(ctx->image);
+  cudaFree(ctx->dToneF); cudaFree(ctx->dTone8);
+  ctx->image = nullptr; ctx->dToneF = nullptr; ctx->dTone8 = nullptr;
+  ctx->W = (int)width; ctx->H = (int)height;
+  if(device_rgba32f)
+  {
+    ctx->image     = (float4*)device_rgba32f;
+    ctx->ownsImage = false;
+  }
+  else
+  {
+    CTX_CHECK(cudaMalloc(&ctx->image, (size_t)width * height * sizeof(float4)));
+    CTX_CHECK(cudaMemsetAsync(ctx->image, 0, (size_t)width * height * sizeof(float4), ctx->stream));
+    ctx->ownsImage = true;
+  }
+  return VKRT_OK;
+}
+
+int vkrt_output_device_ptr(vkrt_ctx* ctx, void** out)
+{
+  if(!ctx || !out || !ctx->image) return VKRT_ERR_STATE;
+  *out = ctx->image;
+  return VKRT_OK;
+}
+
+int vkrt_output_clear(vkrt_ctx* ctx)
+{
+  if(!ctx || !ctx->image) return VKRT_ERR_STATE;
+  cudaSetDevice(ctx->device);
+  CTX_CHECK(cudaMemsetAsync(ctx->image, 0, (size_t)ctx->W * ctx->H * sizeof(float4), ctx->stream));
+  return VKRT_OK;
+}
+
+int vkrt_output_read(vkrt_ctx* ctx, float* host)
+{
+  if(!ctx || !ctx->image || !host) return VKRT_ERR_STATE;
+  cudaSetDevice(ctx->device);
+  CTX_CHECK(cudaMemcpyAsync(host, ctx->image, (size_t)ctx->W * ctx->H * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+  return VKRT_OK;
+}
+
+static int tonemapCommon(vkrt_ctx* ctx, const Tonemapper* tm, float* hostF, uint8_t* host8)
+{
+  if(!ctx || !tm || !ctx->image) return VKRT_ERR_STATE;
+  if(tm->autoExposure != 0)
+    return fail(ctx, VKRT_ERR_INVALID, "tonemap: autoExposure (mip-pyramid luminance) is not implemented yet");
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)ctx->W * ctx->H;
+  if(hostF && !ctx->dToneF) CTX_CHECK(cudaMalloc(&ctx->dToneF, n * sizeof(float4)));
+  if(host8 && !ctx->dTone8) CTX_CHECK(cudaMalloc(&ctx->dTone8, n * sizeof(uchar4)));
+  {
+    ScopedTimer t(ctx, true, T_TONEMAP);
+    launchTonemap(ctx->stream, ctx->image, ctx->W, ctx->H, *tm, hostF ? ctx->dToneF : nullptr, host8 ? ctx->dTone8 : nullptr);
+  }
+  ctx->stats.kernel_launches++;
+  if(hostF) CTX_CHECK(cudaMemcpyAsync(hostF, ctx->dToneF, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  if(host8) CTX_CHECK(cudaMemcpyAsync(host8, ctx->dTone8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->stream));
+  CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+  return VKRT_OK;
+}
+int vkrt_tonemap(vkrt_ctx* ctx, const Tonemapper* tm, uint8_t* host_rgba8) { return tonemapCommon(ctx, tm, nullptr, host_rgba8); }
+int vkrt_tonemap_float(vkrt_ctx* ctx, const Tonemapper* tm, float* host_rgba32f) { return tonemapCommon(ctx, tm, host_rgba32f, nullptr); }
+
+// ---- render --------------------------------------------------------------------------------------------
+static int ensurePixelList(vkrt_ctx* ctx, int tile, int rank, int count)
+{
+  const int key[5] = {ctx->W, ctx->H, tile, rank, count};
+  if(std::memcmp(key, ctx->shardKey, sizeof(key)) == 0 && ctx->dPixelOfLocal)
+    return VKRT_OK;
+  // Tiles are dealt round-robin to the shards; inside a tile pixels are ordered in 8x4 blocks so that a
+  // warp of primary rays covers a compact screen footprint.
+  std::vector<uint32_t> px;
+  px.reserve((size_t)ctx->W * ctx->H / std::max(1, count) + 4096);
+  const int tx = (ctx->W + tile - 1) / tile, ty = (ctx->H + tile - 1) / tile;
+  for(int t = 0; t < tx * ty; t++)
+  {
+    if(count > 1 && (t % count) != rank)
+      continue;
+    const int x0 = (t % tx) * tile, y0 = (t / tx) * tile;
+    const int x1 = std::min(x0 + tile, ctx->W), y1 = std::min(y0 + tile, ctx->H);
+    for(int by = y0; by < y1; by += 4)
+      for(int bx = x0; bx < x1; bx += 8)
+        for(int y = by; y < std::min(by + 4, y1); y++)
+          for(int x = bx; x < std::min(bx + 8, x1); x++)
+            px.push_back((uint32_t)(y * ctx->W + x));
+  }
+  if(px.size() > ctx->pixCapacity)
+  {
+    cudaFree(ctx->dPixelOfLocal);
+    ctx->dPixelOfLocal = nullptr;
+    CTX_CHECK(cudaMalloc(&ctx->dPixelOfLocal, 4 * std::max<size_t>(px.size(), 1)));
+    ctx->pixCapacity = px.size();
+  }
+  if(!px.empty())
+    CTX_CHECK(cudaMemcpyAsync(ctx->dPixelOfLocal, px.data(), 4 * px.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(ctx->shardKey, key, sizeof(key));
+  ctx->wf.numLocalPixels = (uint32_t)px.size();
+  ctx->wf.pixelOfLocal   = ctx->dPixelOfLocal;
+  return VKRT_OK;
+}
+
+static int ensureWavefront(vkrt_ctx* ctx, size_t paths)
+{
+  if(paths <= ctx->wfCapacity)
+    return VKRT_OK;
+  const uint32_t keepLocal = ctx->wf.numLocalPixels;
+  freeWavefront(ctx);
+  Wavefront& w = ctx->wf;
+  const size_t b = paths * sizeof(float4);
+  CTX_CHECK(cudaMalloc(&w.rayO, b)); CTX_CHECK(cudaMalloc(&w.rayD, b)); CTX_CHECK(cudaMalloc(&w.hit, b));
+  CTX_CHECK(cudaMalloc(&w.thr, b)); CTX_CHECK(cudaMalloc(&w.rad, b)); CTX_CHECK(cudaMalloc(&w.absb, b));
+  CTX_CHECK(cudaMalloc(&w.sum, b)); CTX_CHECK(cudaMalloc(&w.shO, b)); CTX_CHECK(cudaMalloc(&w.shD, b));
+  CTX_CHECK(cudaMalloc(&w.shC, b));
+  CTX_CHECK(cudaMalloc(&w.queueCur, 4 * paths)); CTX_CHECK(cudaMalloc(&w.queueNext, 4 * paths));
+  CTX_CHECK(cudaMalloc(&w.counters, 64));
+  CTX_CHECK(cudaMemsetAsync(w.counters, 0, 64, ctx->stream));
+  ctx->wfCapacity        = paths;
+  w.numLocalPixels       = keepLocal;
+  w.pixelOfLocal         = ctx->dPixelOfLocal;
+  return VKRT_OK;
+}
+
+int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const vkrt_render_opts* opts)
+{
+  if(!ctx || !state || num_frames <= 0) return VKRT_ERR_INVALID;
+  if(!ctx->committed) return fail(ctx, VKRT_ERR_STATE, "render: scene not committed");
+  if(!ctx->hasEnv) return fail(ctx, VKRT_ERR_STATE, "render: no environment set (the reference always loads one, src/main.cpp:181)");
+  if(!ctx->image) return fail(ctx, VKRT_ERR_STATE, "render: no output image");
+  if(state->size[0] != ctx->W || state->size[1] != ctx->H)
+    return fail(ctx, VKRT_ERR_INVALID, "render: RtxState.size differs from the output image");
+  if(state->maxSamples < 1 || state->maxDepth < 0)
+    return fail(ctx, VKRT_ERR_INVALID, "render: bad maxSamples/maxDepth");
+  if(state->debugging_mode == VKRT_DBG_HEATMAP)
+    return fail(ctx, VKRT_ERR_INVALID, "render: the clock heat-map debug mode has no wavefront equivalent");
+  cudaSetDevice(ctx->device);
+
+  vkrt_render_opts o{};
+  if(opts) o = *opts;
+  const int  tile     = o.tile_size > 0 ? o.tile_size : 64;
+  const int  shards   = o.shard_count > 1 ? o.shard_count : 1;
+  const int  rank     = shards > 1 ? o.shard_rank : 0;
+  const bool counting = o.count_traversal != 0;
+  const bool timing   = o.profile != 0;  // per-kernel CUDA-event timing
+  if(rank < 0 || rank >= shards)
+    return fail(ctx, VKRT_ERR_INVALID, "render: shard_rank out of range");
+
+  int rc = ensurePixelList(ctx, tile, rank, shards);
+  if(rc != VKRT_OK) return rc;
+  const uint32_t nLocal = ctx->wf.numLocalPixels;
+  if(nLocal == 0)
+    return VKRT_OK;
+  int fif = o.frames_in_flight;
+  if(fif <= 0)
+    fif = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(4u << 20) / nLocal));
+  fif = std::min(fif, num_frames);
+  rc  = ensureWavefront(ctx, (size_t)nLocal * fif);
+  if(rc != VKRT_OK) return rc;
+
+  TraceStats* dstats = ctx->dStats;
+  for(int done = 0; done < num_frames;)
+  {
+    const int batch = std::min(fif, num_frames - done);
+    Wavefront wf    = ctx->wf;
+    wf.numPaths     = nLocal * (uint32_t)batch;
+    FrameParams fp{};
+    fp.state         = *state;
+    fp.state.frame   = state->frame + done;
+    fp.seedMode      = o.seed_mode;
+    fp.framesInBatch = batch;
+    for(int smpl = 0; smpl < state->maxSamples; smpl++)
+    {
+      fp.sampleIndex = smpl;
+      fp.depth       = 0;
+      {
+        ScopedTimer t(ctx, timing, T_RAYGEN);
+        launchRaygen(ctx->stream, ctx->view, wf, fp, ctx->numSMs);
+      }
+      ctx->stats.kernel_launches++;
+      for(int depth = 0; depth < state->maxDepth; depth++)
+      {
+        fp.depth = depth;
+        TraceLaunch L{};
+        L.rayO = wf.rayO; L.rayD = wf.rayD; L.queue = wf.queueCur; L.count = wf.counters + 0; L.cursor = wf.counters + 3;
+        L.hit = wf.hit; L.stats = dstats;
+        {
+          ScopedTimer t(ctx, timing, T_CLOSEST);
+          launchTraceClosest(ctx->stream, ctx->view, L, counting, ctx->numSMs);
+        }
+        {
+          ScopedTimer t(ctx, timing, T_SHADE);
+          launchShade(ctx->stream, ctx->view, wf, fp, dstats, ctx->numSMs);
+        }
+        TraceLaunch S{};
+        S.rayO = wf.shO; S.rayD = wf.shD; S.queue = nullptr; S.count = wf.counters + 2; S.cursor = wf.counters + 4;
+        S.shC = wf.shC; S.rad = wf.rad; S.stats = dstats;
+        {
+          ScopedTimer t(ctx, timing, T_SHADOW);
+          launchTraceShadow(ctx->stream, ctx->view, S, counting, ctx->numSMs);
+        }
+        launchSwapQueues(ctx->stream, wf, dstats);
+        ctx->stats.kernel_launches += 4;
+      }
+      {
+        ScopedTimer t(ctx, timing, T_ACCUM);
+        launchFinishSample(ctx->stream, wf, fp, ctx->numSMs);
+      }
+      ctx->stats.kernel_launches++;
+    }
+    {
+      ScopedTimer t(ctx, timing, T_ACCUM);
+      launchAccumulate(ctx->stream, wf, fp, ctx->image, ctx->numSMs);
+    }
+    ctx->stats.kernel_launches++;
+    done += batch;
+    ctx->stats.frames_rendered += batch;
+    if(ctx->pending.size() > 4096)
+      drainTimers(ctx);
+  }
+  CTX_CHECK(cudaGetLastError());
+  return VKRT_OK;
+}
+
+int vkrt_sync(vkrt_ctx* ctx)
+{
+  if(!ctx) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+  return VKRT_OK;
+}
+
+// ---- diagnostics ------------------------------------------------------------------------------------------
+int vkrt_trace_rays(vkrt_ctx* ctx, const float* rays, uint32_t n, int32_t closest, float* out_hits)
+{
+  if(!ctx || !rays || !out_hits) return VKRT_ERR_INVALID;
+  if(!ctx->committed) return fail(ctx, VKRT_ERR_STATE, "trace_rays: scene not committed");
+  if(n == 0) return VKRT_OK;
+  cudaSetDevice(ctx->device);
+  float4 *dR = nullptr, *dH = nullptr;
+  CTX_CHECK(cudaMalloc(&dR, (size_t)n * 32));
+  CTX_CHECK(cudaMalloc(&dH, (size_t)n * 16));
+  cudaMemcpyAsync(dR, rays, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream);
+  launchTraceProbe(ctx->stream, ctx->view, dR, n, closest != 0, dH);
+  ctx->stats.kernel_launches++;
+  cudaMemcpyAsync(out_hits, dH, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dR); cudaFree(dH);
+  if(e != cudaSuccess)
+  {
+    ctx->err = std::string("trace_rays: ") + cudaGetErrorString(e);
+    return VKRT_ERR_CUDA;
+  }
+  return VKRT_OK;
+}
+
+int vkrt_triangle_ids(vkrt_ctx* ctx, const uint32_t* tri_ids, uint32_t n, uint32_t* out_node_prim)
+{
+  if(!ctx || !tri_ids || !out_node_prim) return VKRT_ERR_INVALID;
+  if(!ctx->committed) return fail(ctx, VKRT_ERR_STATE, "triangle_ids: scene not committed");
+  cudaSetDevice(ctx->device);
+  std::vector<uint2> info(ctx->bvh.numTris);
+  if(!info.empty())
+    CTX_CHECK(cudaMemcpy(info.data(), ctx->bvh.triInfo, sizeof(uint2) * info.size(), cudaMemcpyDeviceToHost));
+  for(uint32_t i = 0; i < n; i++)
+  {
+    if(tri_ids[i] < info.size()) { out_node_prim[2 * i] = info[tri_ids[i]].x; out_node_prim[2 * i + 1] = info[tri_ids[i]].y; }
+    else { out_node_prim[2 * i] = ~0u; out_node_prim[2 * i + 1] = ~0u; }
+  }
+  return VKRT_OK;
+}
+
+int vkrt_get_stats(vkrt_ctx* ctx, vkrt_stats* out)
+{
+  if(!ctx || !out) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+  drainTimers(ctx);
+  TraceStats ts{};
+  CTX_CHECK(cudaMemcpy(&ts, ctx->dStats, sizeof(ts), cudaMemcpyDeviceToHost));
+  ctx->stats.closest_rays  = ts.closestRays;
+  ctx->stats.shadow_rays   = ts.shadowRays;
+  ctx->stats.nodes_visited = ts.nodesVisited;
+  ctx->stats.tris_tested   = ts.trisTested;
+  *out = ctx->stats;
+  return VKRT_OK;
+}
+
+int vkrt_reset_stats(vkrt_ctx* ctx)
+{
+  if(!ctx) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+  drainTimers(ctx);
+  CTX_CHECK(cudaMemset(ctx->dStats, 0, sizeof(TraceStats)));
+  vkrt_stats keep = ctx->stats;
+  ctx->stats      = vkrt_stats{};
+  ctx->stats.ms_build = keep.ms_build; ctx->stats.num_triangles = keep.num_triangles; ctx->stats.num_bvh_nodes = keep.num_bvh_nodes;
+  ctx->stats.num_instances = keep.num_instances; ctx->stats.has_non_opaque = keep.has_non_opaque;
+  return VKRT_OK;
+}
+
+}  // extern "C"

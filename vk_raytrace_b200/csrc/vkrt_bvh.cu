@@ -1,0 +1,411 @@
+// vkrt_bvh.cu -- GPU acceleration-structure build for sm_100a.
+//
+// Replaces AccelStructure::createBottomLevelAS / createTopLevelAS of the reference
+// (src/accelstruct.cpp:110-162), where the Vulkan driver builds an opaque two-level
+// BVH.  B200 design: 180 GB of HBM makes instancing-by-reference unnecessary for the
+// scene sizes of this path, so every instance is flattened to world space once and a
+// single-level BVH2 is built over all triangles:
+//   1. flatten      instance x triangle -> world-space triangle, bounds, centroid
+//   2. morton       63-bit Morton code of the centroid
+//   3. sort         radix sort (CUB) of (code, triangle id)
+//   4. hierarchy    Karras 2012 binary radix tree, one thread per internal node
+//   5. refit        bottom-up AABB + SAH cost with atomic arrival flags
+//   6. emit         64-byte two-child-box nodes, optional SAH leaf collapse
+// Instance flag semantics (FORCE_OPAQUE, CULL_DISABLE) are carried per triangle.
+#include <cub/cub.cuh>
+#include <cfloat>
+#include "vkrt_device.cuh"
+#include "vkrt_internal.h"
+
+namespace vkrt {
+
+__device__ __forceinline__ uint32_t orderedFromFloat(float f)
+{
+  uint32_t u = __float_as_uint(f);
+  return u ^ ((uint32_t)((int32_t)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float floatFromOrdered(uint32_t u)
+{
+  u ^= ((u >> 31) - 1u) | 0x80000000u;
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ uint64_t expandBits21(uint32_t v)
+{
+  uint64_t x = v & 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+// ---- 1. flatten ----------------------------------------------------------------------
+__global__ void flattenKernel(const InstanceXform* __restrict__ inst, const uint32_t* __restrict__ instTriOffset, uint32_t numInst,
+                              const InstanceData* __restrict__ geo, uint32_t numTris, float4* __restrict__ wtri,
+                              uint2* __restrict__ triInfo, uint32_t* __restrict__ boundsOrdered /*6*/)
+{
+  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  float3   c   = f3(0.f);
+  bool     ok  = gid < numTris;
+  if(ok)
+  {
+    // instance lookup: last i with instTriOffset[i] <= gid
+    uint32_t lo = 0, hi = numInst;
+    while(hi - lo > 1)
+    {
+      uint32_t mid = (lo + hi) >> 1;
+      if(instTriOffset[mid] <= gid)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    const InstanceXform& I    = inst[lo];
+    uint32_t             prim = gid - I.triOffset;
+    const InstanceData   g    = geo[I.primMesh];
+    const uint32_t*      idx  = reinterpret_cast<const uint32_t*>(g.indexAddress) + 3ull * prim;
+    const VertexAttributes* vtx = reinterpret_cast<const VertexAttributes*>(g.vertexAddress);
+    const float* pa = vtx[idx[0]].position;
+    const float* pb = vtx[idx[1]].position;
+    const float* pc = vtx[idx[2]].position;
+    float3 v0 = xformPoint(I.o2w, f3(pa[0], pa[1], pa[2]));
+    float3 v1 = xformPoint(I.o2w, f3(pb[0], pb[1], pb[2]));
+    float3 v2 = xformPoint(I.o2w, f3(pc[0], pc[1], pc[2]));
+    wtri[3ull * gid + 0] = f4(v0, __uint_as_float(I.flags));
+    wtri[3ull * gid + 1] = f4(v1, __uint_as_float(gid));
+    wtri[3ull * gid + 2] = f4(v2, 0.f);
+    triInfo[gid]         = make_uint2(lo, prim);
+    float3 lo3 = f3(fminf(v0.x, fminf(v1.x, v2.x)), fminf(v0.y, fminf(v1.y, v2.y)), fminf(v0.z, fminf(v1.z, v2.z)));
+    float3 hi3 = f3(fmaxf(v0.x, fmaxf(v1.x, v2.x)), fmaxf(v0.y, fmaxf(v1.y, v2.y)), fmaxf(v0.z, fmaxf(v1.z, v2.z)));
+    c          = (lo3 + hi3) * 0.5f;
+  }
+  // centroid bounds: warp reduce then one atomic per warp
+  float mnx = ok ? c.x : FLT_MAX, mny = ok ? c.y : FLT_MAX, mnz = ok ? c.z : FLT_MAX;
+  float mxx = ok ? c.x : -FLT_MAX, mxy = ok ? c.y : -FLT_MAX, mxz = ok ? c.z : -FLT_MAX;
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1)
+  {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+    mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mnz = fminf(mnz, __shfl_xor_sync(0xffffffffu, mnz, o));
+    mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    mxz = fmaxf(mxz, __shfl_xor_sync(0xffffffffu, mxz, o));
+  }
+  if((threadIdx.x & 31) == 0 && mnx <= mxx)
+  {
+    atomicMin(&boundsOrdered[0], orderedFromFloat(mnx));
+    atomicMin(&boundsOrdered[1], orderedFromFloat(mny));
+    atomicMin(&boundsOrdered[2], orderedFromFloat(mnz));
+    atomicMax(&boundsOrdered[3], orderedFromFloat(mxx));
+    atomicMax(&boundsOrdered[4], orderedFromFloat(mxy));
+    atomicMax(&boundsOrdered[5], orderedFromFloat(mxz));
+  }
+}
+
+// ---- 2. morton ------------------------------------------------------------------------
+__global__ void mortonKernel(const float4* __restrict__ wtri, uint32_t numTris, const uint32_t* __restrict__ boundsOrdered,
+                             uint64_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+  uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
+  if(gid >= numTris)
+    return;
+  float3 bmin = f3(floatFromOrdered(boundsOrdered[0]), floatFromOrdered(boundsOrdered[1]), floatFromOrdered(boundsOrdered[2]));
+  float3 bmax = f3(floatFromOrdered(boundsOrdered[3]), floatFromOrdered(boundsOrdered[4]), floatFromOrdered(boundsOrdered[5]));
+  float3 v0 = f3(wtri[3ull * gid]), v1 = f3(wtri[3ull * gid + 1]), v2 = f3(wtri[3ull * gid + 2]);
+  float3 lo3 = f3(fminf(v0.x, fminf(v1.x, v2.x)), fminf(v0.y, fminf(v1.y, v2.y)), fminf(v0.z, fminf(v1.z, v2.z)));
+  float3 hi3 = f3(fmaxf(v0.x, fmaxf(v1.x, v2.x)), fmaxf(v0.y, fmaxf(v1.y, v2.y)), fmaxf(v0.z, fmaxf(v1.z, v2.z)));
+  float3 c   = (lo3 + hi3) * 0.5f;
+  float3 ext = bmax - bmin;
+  const float scale = 2097151.0f;  // 2^21 - 1
+  float fx = ext.x > 0.f ? (c.x - bmin.x) / ext.x : 0.f;
+  float fy = ext.y > 0.f ? (c.y - bmin.y) / ext.y : 0.f;
+  float fz = ext.z > 0.f ? (c.z - bmin.z) / ext.z : 0.f;
+  uint32_t ix = (uint32_t)fminf(fmaxf(fx * scale, 0.f), scale);
+  uint32_t iy = (uint32_t)fminf(fmaxf(fy * scale, 0.f), scale);
+  uint32_t iz = (uint32_t)fminf(fmaxf(fz * scale, 0.f), scale);
+  keys[gid]   = (expandBits21(ix) << 2) | (expandBits21(iy) << 1) | expandBits21(iz);
+  vals[gid]   = gid;
+}
+
+// ---- 4. hierarchy (Karras 2012) ----------------------------------------------------------
+__device__ __forceinline__ int deltaKeys(const uint64_t* __restrict__ keys, int n, int i, int j)
+{
+  if(j < 0 || j >= n)
+    return -1;
+  uint64_t a = keys[i], b = keys[j];
+  if(a == b)
+    return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+  return __clzll((long long)(a ^ b));
+}
+
+// child codes during the build: >= 0 internal node index, < 0 : ~leafIndex
+__global__ void hierarchyKernel(const uint64_t* __restrict__ keys, int n, int2* __restrict__ children, int2* __restrict__ ranges,
+                                int* __restrict__ parentInner, int* __restrict__ parentLeaf)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n - 1)
+    return;
+  int d     = (deltaKeys(keys, n, i, i + 1) - deltaKeys(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin  = deltaKeys(keys, n, i, i - d);
+  int lmax  = 2;
+  while(deltaKeys(keys, n, i, i + lmax * d) > dmin)
+    lmax <<= 1;
+  int l = 0;
+  for(int t = lmax >> 1; t >= 1; t >>= 1)
+    if(deltaKeys(keys, n, i, i + (l + t) * d) > dmin)
+      l += t;
+  int j     = i + l * d;
+  int dnode = deltaKeys(keys, n, i, j);
+  int s     = 0;
+  int t     = l;
+  do
+  {
+    t = (t + 1) >> 1;
+    if(deltaKeys(keys, n, i, i + (s + t) * d) > dnode)
+      s += t;
+  } while(t > 1);
+  int gamma = i + s * d + min(d, 0);
+  int first = min(i, j), last = max(i, j);
+  int left  = (first == gamma) ? ~gamma : gamma;
+  int right = (last == gamma + 1) ? ~(gamma + 1) : (gamma + 1);
+  children[i] = make_int2(left, right);
+  ranges[i]   = make_int2(first, last);
+  if(left >= 0) parentInner[left] = i; else parentLeaf[~left] = i;
+  if(right >= 0) parentInner[right] = i; else parentLeaf[~right] = i;
+  if(i == 0)
+    parentInner[0] = -1;
+}
+
+// ---- 5. leaves + refit ----------------------------------------------------------------------
+struct Box
+{
+  float lo[3], hi[3];
+};
+// Boxes / costs written by other blocks during the bottom-up pass must not be read
+// through a stale L1 line: load them with ld.global.cg.
+__device__ __forceinline__ Box loadBoxCg(const Box* p)
+{
+  Box          b;
+  const float* f = reinterpret_cast<const float*>(p);
+#pragma unroll
+  for(int k = 0; k < 3; k++)
+  {
+    b.lo[k] = __ldcg(f + k);
+    b.hi[k] = __ldcg(f + 3 + k);
+  }
+  return b;
+}
+__device__ __forceinline__ float boxArea(const Box& b)
+{
+  float ex = b.hi[0] - b.lo[0], ey = b.hi[1] - b.lo[1], ez = b.hi[2] - b.lo[2];
+  return 2.0f * (ex * ey + ey * ez + ez * ex);
+}
+
+__global__ void refitKernel(const float4* __restrict__ wtri, const uint32_t* __restrict__ sortedVals, int n, float4* __restrict__ tris,
+                            const int2* __restrict__ children, const int* __restrict__ parentInner, const int* __restrict__ parentLeaf,
+                            Box* __restrict__ leafBox, Box* __restrict__ nodeBox, float* __restrict__ nodeCost, int* __restrict__ nodeDepth,
+                            uint32_t* __restrict__ collapsed, const int2* __restrict__ ranges, int* __restrict__ flags, int collapseMax,
+                            int* __restrict__ maxDepthOut)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if(j >= n)
+    return;
+  uint32_t gid = sortedVals[j];
+  float4   a = wtri[3ull * gid], b = wtri[3ull * gid + 1], c = wtri[3ull * gid + 2];
+  tris[3ull * j] = a; tris[3ull * j + 1] = b; tris[3ull * j + 2] = c;
+  Box bx;
+  bx.lo[0] = fminf(a.x, fminf(b.x, c.x)); bx.lo[1] = fminf(a.y, fminf(b.y, c.y)); bx.lo[2] = fminf(a.z, fminf(b.z, c.z));
+  bx.hi[0] = fmaxf(a.x, fmaxf(b.x, c.x)); bx.hi[1] = fmaxf(a.y, fmaxf(b.y, c.y)); bx.hi[2] = fmaxf(a.z, fmaxf(b.z, c.z));
+  leafBox[j] = bx;
+  if(n == 1)
+    return;
+  const float Ct = 1.0f, Ci = 1.2f;
+  int node = parentLeaf[j];
+  __threadfence();
+  while(node >= 0)
+  {
+    if(atomicAdd(&flags[node], 1) == 0)
+      return;  // first arrival: the sibling subtree is not finished yet
+    __threadfence();
+    int2 ch = children[node];
+    Box  l  = loadBoxCg(ch.x >= 0 ? &nodeBox[ch.x] : &leafBox[~ch.x]);
+    Box  r  = loadBoxCg(ch.y >= 0 ? &nodeBox[ch.y] : &leafBox[~ch.y]);
+    Box  u;
+#pragma unroll
+    for(int k = 0; k < 3; k++)
+    {
+      u.lo[k] = fminf(l.lo[k], r.lo[k]);
+      u.hi[k] = fmaxf(l.hi[k], r.hi[k]);
+    }
+    nodeBox[node] = u;
+    float cl = ch.x >= 0 ? __ldcg(&nodeCost[ch.x]) : Ct * boxArea(l);
+    float cr = ch.y >= 0 ? __ldcg(&nodeCost[ch.y]) : Ct * boxArea(r);
+    int   dl = ch.x >= 0 ? __ldcg(&nodeDepth[ch.x]) : 0;
+    int   dr = ch.y >= 0 ? __ldcg(&nodeDepth[ch.y]) : 0;
+    int2  rg    = ranges[node];
+    int   count = rg.y - rg.x + 1;
+    float A     = boxArea(u);
+    float cInner = Ci * A + cl + cr;
+    float cLeaf  = Ct * A * (float)count;
+    bool  col    = collapseMax > 1 && count <= collapseMax && cLeaf <= cInner;
+    collapsed[node] = col ? 1u : 0u;
+    nodeCost[node]  = col ? cLeaf : cInner;
+    int depth       = col ? 0 : (max(dl, dr) + 1);
+    nodeDepth[node] = depth;
+    if(parentInner[node] < 0)
+      *maxDepthOut = depth;
+    __threadfence();
+    node = parentInner[node];
+  }
+}
+
+// ---- 6. emit ---------------------------------------------------------------------------
+__global__ void emitKernel(int n, const int2* __restrict__ children, const int2* __restrict__ ranges, const Box* __restrict__ leafBox,
+                           const Box* __restrict__ nodeBox, const uint32_t* __restrict__ collapsed, float4* __restrict__ nodes)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= max(n - 1, 1))
+    return;
+  Box      b0, b1;
+  uint32_t c0, c1;
+  if(n == 1)
+  {
+    // a single triangle: both children are the same leaf (the duplicate candidate
+    // loses the tie-break, so it is harmless)
+    b0 = leafBox[0];
+    b1 = b0;
+    c0 = kLeafBit | 0u;
+    c1 = c0;
+  }
+  else
+  {
+    int2 ch = children[i];
+    auto enc = [&](int c, Box& bx) -> uint32_t {
+      if(c < 0)
+      {
+        bx = leafBox[~c];
+        return kLeafBit | (uint32_t)(~c);
+      }
+      bx = nodeBox[c];
+      if(collapsed[c])
+      {
+        int2 rg = ranges[c];
+        return kLeafBit | ((uint32_t)(rg.y - rg.x) << kLeafCntSh) | (uint32_t)rg.x;
+      }
+      return (uint32_t)c;
+    };
+    c0 = enc(ch.x, b0);
+    c1 = enc(ch.y, b1);
+  }
+  nodes[4ull * i + 0] = f4(b0.lo[0], b0.hi[0], b0.lo[1], b0.hi[1]);
+  nodes[4ull * i + 1] = f4(b1.lo[0], b1.hi[0], b1.lo[1], b1.hi[1]);
+  nodes[4ull * i + 2] = f4(b0.lo[2], b0.hi[2], b1.lo[2], b1.hi[2]);
+  nodes[4ull * i + 3] = f4(__uint_as_float(c0), __uint_as_float(c1), 0.f, 0.f);
+}
+
+// numTris == 0: the trace kernels never traverse (they test SceneView::numTris); the node
+// is only written so that the buffer is defined.
+__global__ void emptySceneKernel(float4* nodes)
+{
+  nodes[0] = f4(0.f, 0.f, 0.f, 0.f);
+  nodes[1] = f4(0.f, 0.f, 0.f, 0.f);
+  nodes[2] = f4(0.f, 0.f, 0.f, 0.f);
+  nodes[3] = f4(__uint_as_float(kLeafBit), __uint_as_float(kLeafBit), 0.f, 0.f);
+}
+
+#define CK(x)                                                                                                          \
+  do                                                                                                                   \
+  {                                                                                                                    \
+    cudaError_t e_ = (x);                                                                                              \
+    if(e_ != cudaSuccess)                                                                                              \
+    {                                                                                                                  \
+      err = std::string(#x) + ": " + cudaGetErrorString(e_);                                                           \
+      goto fail;                                                                                                       \
+    }                                                                                                                  \
+  } while(0)
+
+// Host driver.  All temporaries are freed before returning; nodes/tris/triInfo are owned by the caller.
+bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* dInstTriOffset, uint32_t numInst, const InstanceData* dGeo,
+              uint32_t numTris, int buildMode, BvhResult& out, std::string& err, uint64_t* launches)
+{
+  out = BvhResult{};
+  float4*   wtri = nullptr;
+  uint32_t* bounds = nullptr;
+  uint64_t *keysA = nullptr, *keysB = nullptr;
+  uint32_t *valsA = nullptr, *valsB = nullptr;
+  void*     cubTemp = nullptr;
+  int2 *children = nullptr, *ranges = nullptr;
+  int *parentInner = nullptr, *parentLeaf = nullptr, *flags = nullptr, *nodeDepth = nullptr, *maxDepthDev = nullptr;
+  Box *leafBox = nullptr, *nodeBox = nullptr;
+  float*    nodeCost = nullptr;
+  uint32_t* collapsed = nullptr;
+  const int B = 256;
+  uint32_t  numNodes = numTris > 1 ? numTris - 1 : 1;
+
+  CK(cudaMalloc(&out.nodes, sizeof(float4) * 4ull * numNodes));
+  CK(cudaMalloc(&out.tris, sizeof(float4) * 3ull * (numTris ? numTris : 1)));
+  CK(cudaMalloc(&out.triInfo, sizeof(uint2) * (numTris ? numTris : 1)));
+  out.numNodes = numNodes;
+  out.numTris  = numTris;
+  if(numTris == 0)
+  {
+    emptySceneKernel<<<1, 1, 0, stream>>>(out.nodes);
+    if(launches) (*launches)++;
+    CK(cudaStreamSynchronize(stream));
+    return true;
+  }
+  {
+    size_t n = numTris;
+    CK(cudaMalloc(&wtri, sizeof(float4) * 3 * n));
+    CK(cudaMalloc(&bounds, 6 * sizeof(uint32_t)));
+    CK(cudaMalloc(&keysA, 8 * n)); CK(cudaMalloc(&keysB, 8 * n));
+    CK(cudaMalloc(&valsA, 4 * n)); CK(cudaMalloc(&valsB, 4 * n));
+    CK(cudaMalloc(&children, sizeof(int2) * n)); CK(cudaMalloc(&ranges, sizeof(int2) * n));
+    CK(cudaMalloc(&parentInner, 4 * n)); CK(cudaMalloc(&parentLeaf, 4 * n)); CK(cudaMalloc(&flags, 4 * n));
+    CK(cudaMalloc(&nodeDepth, 4 * n)); CK(cudaMalloc(&maxDepthDev, 4));
+    CK(cudaMalloc(&leafBox, sizeof(Box) * n)); CK(cudaMalloc(&nodeBox, sizeof(Box) * n));
+    CK(cudaMalloc(&nodeCost, 4 * n)); CK(cudaMalloc(&collapsed, 4 * n));
+
+    uint32_t initB[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+    CK(cudaMemcpyAsync(bounds, initB, sizeof(initB), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemsetAsync(flags, 0, 4 * n, stream));
+    CK(cudaMemsetAsync(collapsed, 0, 4 * n, stream));
+    CK(cudaMemsetAsync(maxDepthDev, 0, 4, stream));
+    uint32_t grid = (uint32_t)((n + B - 1) / B);
+    flattenKernel<<<grid, B, 0, stream>>>(dInst, dInstTriOffset, numInst, dGeo, numTris, wtri, out.triInfo, bounds);
+    mortonKernel<<<grid, B, 0, stream>>>(wtri, numTris, bounds, keysA, valsA);
+    size_t tempBytes = 0;
+    cub::DoubleBuffer<uint64_t> dk(keysA, keysB);
+    cub::DoubleBuffer<uint32_t> dv(valsA, valsB);
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, dk, dv, (int)n, 0, 63, stream));
+    CK(cudaMalloc(&cubTemp, tempBytes ? tempBytes : 16));
+    CK(cub::DeviceRadixSort::SortPairs(cubTemp, tempBytes, dk, dv, (int)n, 0, 63, stream));
+    const uint64_t* sk = dk.Current();
+    const uint32_t* sv = dv.Current();
+    if(n > 1)
+      hierarchyKernel<<<grid, B, 0, stream>>>(sk, (int)n, children, ranges, parentInner, parentLeaf);
+    int collapseMax = buildMode == VKRT_BUILD_LBVH_COLLAPSED ? 8 : 1;
+    refitKernel<<<grid, B, 0, stream>>>(wtri, sv, (int)n, out.tris, children, parentInner, parentLeaf, leafBox, nodeBox, nodeCost,
+                                       nodeDepth, collapsed, ranges, flags, collapseMax, maxDepthDev);
+    emitKernel<<<grid, B, 0, stream>>>((int)n, children, ranges, leafBox, nodeBox, collapsed, out.nodes);
+    if(launches) (*launches) += 5 + 7;  // ours + the radix-sort passes of the library
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&out.maxDepth, maxDepthDev, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+  cudaFree(wtri); cudaFree(bounds); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB); cudaFree(cubTemp);
+  cudaFree(children); cudaFree(ranges); cudaFree(parentInner); cudaFree(parentLeaf); cudaFree(flags); cudaFree(nodeDepth);
+  cudaFree(maxDepthDev); cudaFree(leafBox); cudaFree(nodeBox); cudaFree(nodeCost); cudaFree(collapsed);
+  return true;
+fail:
+  cudaFree(wtri); cudaFree(bounds); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB); cudaFree(cubTemp);
+  cudaFree(children); cudaFree(ranges); cudaFree(parentInner); cudaFree(parentLeaf); cudaFree(flags); cudaFree(nodeDepth);
+  cudaFree(maxDepthDev); cudaFree(leafBox); cudaFree(nodeBox); cudaFree(nodeCost); cudaFree(collapsed);
+  cudaFree(out.nodes); cudaFree(out.tris); cudaFree(out.triInfo);
+  out = BvhResult{};
+  return false;
+}
+
+}  // namespace vkrt

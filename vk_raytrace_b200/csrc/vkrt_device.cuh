@@ -1,0 +1,89 @@
+// vkrt_device.cuh -- device-side views of the scene, the BVH and the wavefront state.
+//
+// HBM layout (DESIGN.md "data layout"):
+//   BVH2 node     64 B = 4 x float4  {c0.lo.x c0.hi.x c0.lo.y c0.hi.y | c1.lo.x c1.hi.x c1.lo.y c1.hi.y |
+//                                      c0.lo.z c0.hi.z c1.lo.z c1.hi.z | child0 child1 - -}
+//   triangle      48 B = 3 x float4  {v0.xyz flags | v1.xyz triId | v2.xyz -}   (world space, BVH leaf order)
+//   ray           32 B = 2 x float4  {o.xyz tmax | d.xyz seed}
+//   hit           16 B = 1 x float4  {t u v triId}
+//   path state    48 B = 3 x float4  {throughput.xyz seed | radiance.xyz flags | absorption.xyz sampleSum-slot}
+#pragma once
+#include "vkrt_math.cuh"
+#include "../../include/vkrt_host_device.h"
+
+namespace vkrt {
+
+enum TriFlags : uint32_t { TRI_OPAQUE = 1u, TRI_CULL_DISABLE = 2u, TRI_FLIP_FACING = 4u };
+
+// child encoding in BVH nodes
+constexpr uint32_t kLeafBit   = 0x80000000u;
+constexpr uint32_t kLeafCntSh = 28;           // bits 28..30: triangle count - 1
+constexpr uint32_t kLeafMask  = 0x0fffffffu;  // bits 0..27 : first triangle slot
+
+struct InstanceXform  // one per TLAS-equivalent node (src/accelstruct.cpp:132-157), 112 B
+{
+  float    o2w[12];  // row-major 3x4
+  float    w2o[12];
+  uint32_t primMesh;
+  uint32_t flags;
+  uint32_t triOffset;
+  uint32_t triCount;
+};
+
+struct TexDesc
+{
+  const uchar4* data;
+  int32_t       w, h;
+  int32_t       linear;  // mag filter (LOD 0)
+  int32_t       wrapS, wrapT;  // 0 repeat 1 clamp 2 mirror
+  int32_t       _pad;
+};
+
+struct SceneView
+{
+  // traversal
+  const float4* nodes;     // 4 per node
+  const float4* tris;      // 3 per triangle, leaf order
+  const uint2*  triInfo;   // by flattened triangle id: {node(instance), prim}
+  // shading
+  const InstanceXform*     instances;
+  const InstanceData*      geoInfo;    // per primMesh: reference layout, CUDA pointers
+  const GltfShadeMaterial* materials;
+  const Light*             lights;
+  const TexDesc*           textures;
+  const float4*            envPixels;
+  const EnvAccel*          envAccel;
+  int32_t                  envW, envH;
+  uint32_t                 numTris;
+  uint32_t                 hasNonOpaque;
+  SceneCamera              camera;
+  SunAndSky                sunsky;
+};
+
+// Wavefront buffers (SoA, one entry per path in flight).
+struct Wavefront
+{
+  float4*   rayO;      // o.xyz, tmax
+  float4*   rayD;      // d.xyz, seed bits (seed at the time of the trace call)
+  float4*   hit;       // t,u,v,tri
+  float4*   thr;       // throughput.xyz, seed bits
+  float4*   rad;       // radiance.xyz, flags
+  float4*   absb;      // absorption.xyz, -
+  float4*   sum;       // per-pixel sample sum for maxSamples > 1 (xyz), -
+  float4*   shO;       // shadow rays: o.xyz, tmax
+  float4*   shD;       // d.xyz, seed bits
+  float4*   shC;       // contribution.xyz, path id bits
+  uint32_t* queueCur;  // path ids to process this bounce
+  uint32_t* queueNext;
+  uint32_t* counters;  // [0] cur count, [1] next count, [2] shadow count, [3] trace cursor, [4] shadow cursor
+  const uint32_t* pixelOfLocal;  // local pixel slot -> y*W + x
+  uint32_t  numLocalPixels;
+  uint32_t  numPaths;  // numLocalPixels * framesInFlight
+};
+
+struct TraceStats  // device counters
+{
+  unsigned long long closestRays, shadowRays, nodesVisited, trisTested;
+};
+
+}  // namespace vkrt

@@ -1,0 +1,66 @@
+// vkrt_internal.h -- host-side declarations shared by the translation units of libvkrt_b200.
+#pragma once
+#include <string>
+#include <cuda_runtime.h>
+#include "../../include/vkrt_b200.h"
+
+namespace vkrt {
+
+struct InstanceXform;
+struct SceneView;
+struct Wavefront;
+struct TraceStats;
+
+struct BvhResult
+{
+  float4*  nodes    = nullptr;
+  float4*  tris     = nullptr;
+  uint2*   triInfo  = nullptr;
+  uint32_t numNodes = 0;
+  uint32_t numTris  = 0;
+  int      maxDepth = 0;
+};
+
+// vkrt_bvh.cu
+bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* dInstTriOffset, uint32_t numInst, const InstanceData* dGeo,
+              uint32_t numTris, int buildMode, BvhResult& out, std::string& err, uint64_t* launches);
+
+// vkrt_trace.cu
+struct TraceLaunch
+{
+  const float4*   rayO;
+  const float4*   rayD;
+  const uint32_t* queue;      // ray slots to trace (nullptr: identity)
+  const uint32_t* count;      // device count of queue entries
+  uint32_t*       cursor;     // device work cursor (zeroed by the caller)
+  float4*         hit;        // closest: per ray slot {t,u,v,tri}
+  // shadow resolve (any-hit): adds contribution to rad[path] when unoccluded
+  const float4*   shC;
+  float4*         rad;
+  TraceStats*     stats;      // nullptr unless counting
+};
+void launchTraceClosest(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, bool count, int numSMs);
+void launchTraceShadow(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, bool count, int numSMs);
+void launchTraceProbe(cudaStream_t s, const SceneView& scene, const float4* rays, uint32_t n, bool closest, float4* out);
+
+// vkrt_shade.cu
+struct FrameParams
+{
+  RtxState state;       // frame = first frame of the batch
+  int32_t  seedMode;
+  int32_t  framesInBatch;
+  int32_t  sampleIndex; // 0..maxSamples-1
+  int32_t  depth;
+};
+void launchRaygen(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, int numSMs);
+void launchShade(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs);
+void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, int numSMs);
+void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, int numSMs);
+void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats);
+void launchTonemap(cudaStream_t s, const float4* image, int w, int h, const Tonemapper& tm, float4* outF, uchar4* out8);
+
+// vkrt_host.cpp
+void buildEnvAccelHost(const float* rgba, uint32_t w, uint32_t h, EnvAccel* out, float* integral, float* average);
+bool invertAffine(const float* m16, float* inv16);
+
+}  // namespace vkrt

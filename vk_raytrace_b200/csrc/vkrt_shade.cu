@@ -1,0 +1,660 @@
+// vkrt_shade.cu -- wavefront kernels around the traversal: ray generation, the
+// shade / next-bounce kernel, sample finish, accumulation and the tonemapper.
+//
+// Together they replace the reference's per-pixel megakernel
+//   shaders/pathtrace.comp:87-134 / pathtrace.rgen:60-108   (seed, sample loop, accumulate)
+//   shaders/pathtrace.glsl:97-387                           (DirectLight, PathTrace, samplePixel)
+//   shaders/shade_state.glsl:63-145, gltf_material.glsl:52-193, env_sampling.glsl:38-135,
+//   shaders/punctual.glsl:28-51, post.frag:98-147 + tonemapping.glsl:24-65
+// The megakernel's `for depth` loop becomes one trace + one shade launch per bounce;
+// every path carries its RNG seed and consumes draws in the reference's order
+// (SURVEY.md App. B), so results do not depend on scheduling.
+#include "vkrt_device.cuh"
+#include "vkrt_texture.cuh"
+#include "vkrt_bsdf.cuh"
+#include "vkrt_sunsky.cuh"
+#include "vkrt_internal.h"
+
+namespace vkrt {
+
+constexpr int kShadeBlock = 128;
+
+// ---- ray generation: pathtrace.comp:97 / pathtrace.rgen:72 + pathtrace.glsl:348-376 -------------------
+__global__ void __launch_bounds__(256) raygenKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
+                                                    const __grid_constant__ FrameParams fp)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if(p == 0)
+  {
+    wf.counters[0] = wf.numPaths;
+    wf.counters[1] = 0;
+    wf.counters[2] = 0;
+    wf.counters[3] = 0;
+    wf.counters[4] = 0;
+  }
+  if(p >= wf.numPaths)
+    return;
+  const uint32_t f     = p / wf.numLocalPixels;
+  const uint32_t lp    = p - f * wf.numLocalPixels;
+  const uint32_t pixel = wf.pixelOfLocal[lp];
+  const int      W = fp.state.size[0], H = fp.state.size[1];
+  const int      px = (int)(pixel % (uint32_t)W), py = (int)(pixel / (uint32_t)W);
+  const int      frame = fp.state.frame + (int)f;
+
+  uint32_t seed;
+  if(fp.sampleIndex == 0)
+  {
+    seed = (fp.seedMode == VKRT_SEED_RAYQUERY) ? tea((uint32_t)(W * py + px), (uint32_t)(frame * fp.state.maxSamples))
+                                               : tea((uint32_t)py * (uint32_t)W + (uint32_t)px, (uint32_t)frame);
+    wf.sum[p] = f4(0.f, 0.f, 0.f, 0.f);
+  }
+  else
+  {
+    seed = __float_as_uint(wf.thr[p].w);  // the stream continues across the maxSamples loop
+  }
+
+  float2 jitter;
+  if(frame == 0)
+    jitter = f2(0.5f, 0.5f);
+  else
+  {
+    float jx = rnd(seed);
+    float jy = rnd(seed);
+    jitter   = f2(jx, jy);
+  }
+  const float2 pixelCenter = f2((float)px + jitter.x, (float)py + jitter.y);
+  const float2 inUV        = f2(pixelCenter.x / (float)W, pixelCenter.y / (float)H);
+  const float2 d           = f2(inUV.x * 2.0f - 1.0f, inUV.y * 2.0f - 1.0f);
+
+  const SceneCamera& cam = sc.camera;
+  float4 origin    = mulMV(cam.viewInverse, f4(0, 0, 0, 1));
+  float4 target    = mulMV(cam.projInverse, f4(d.x, d.y, 1, 1));
+  float4 direction = mulMV(cam.viewInverse, f4(normalize(f3(target)), 0));
+
+  float3 focalPoint  = cam.focalDist * f3(direction);
+  float  cam_r1      = rnd(seed) * kTwoPi;
+  float  cam_r2      = rnd(seed) * cam.aperture;
+  float4 cam_right   = mulMV(cam.viewInverse, f4(1, 0, 0, 0));
+  float4 cam_up      = mulMV(cam.viewInverse, f4(0, 1, 0, 0));
+  float3 aperturePos = (cosf(cam_r1) * f3(cam_right) + sinf(cam_r1) * f3(cam_up)) * sqrtf(cam_r2);
+  float3 rayDir      = normalize(focalPoint - aperturePos);
+
+  wf.rayO[p]     = f4(f3(origin) + aperturePos, kInfinity);
+  wf.rayD[p]     = f4(rayDir, __uint_as_float(seed));
+  wf.thr[p]      = f4(1.f, 1.f, 1.f, __uint_as_float(seed));
+  wf.rad[p]      = f4(0.f, 0.f, 0.f, 0.f);
+  wf.absb[p]     = f4(0.f, 0.f, 0.f, 0.f);
+  wf.queueCur[p] = p;
+}
+
+// ---- shading state from the hit: shade_state.glsl:63-145 -----------------------------------------------
+struct HitGeom
+{
+  float3   position, normal, tangent, bitangent, color;
+  float2   texCoord;
+  uint32_t matIndex;
+};
+
+VKRT_D HitGeom loadHitGeom(const SceneView& sc, uint32_t triId, float bu, float bv)
+{
+  HitGeom g;
+  const uint2          info = __ldg(&sc.triInfo[triId]);
+  const InstanceXform& I    = sc.instances[info.x];
+  const InstanceData   geo  = sc.geoInfo[I.primMesh];
+  const uint32_t*      idx  = reinterpret_cast<const uint32_t*>(geo.indexAddress) + 3ull * info.y;
+  const uint4*         vtx  = reinterpret_cast<const uint4*>(geo.vertexAddress);  // 32-B vertices as 2 x 16 B
+  const uint32_t       i0 = __ldg(idx), i1 = __ldg(idx + 1), i2 = __ldg(idx + 2);
+  const uint4 a0 = __ldg(&vtx[2ull * i0]), a1 = __ldg(&vtx[2ull * i0 + 1]);
+  const uint4 b0 = __ldg(&vtx[2ull * i1]), b1 = __ldg(&vtx[2ull * i1 + 1]);
+  const uint4 c0 = __ldg(&vtx[2ull * i2]), c1 = __ldg(&vtx[2ull * i2 + 1]);
+  // VertexAttributes: {pos.xyz, normal | uv.xy, tangent, color}
+  const float3 bary = f3(1.0f - bu - bv, bu, bv);
+  const float3 pos0 = f3(__uint_as_float(a0.x), __uint_as_float(a0.y), __uint_as_float(a0.z));
+  const float3 pos1 = f3(__uint_as_float(b0.x), __uint_as_float(b0.y), __uint_as_float(b0.z));
+  const float3 pos2 = f3(__uint_as_float(c0.x), __uint_as_float(c0.y), __uint_as_float(c0.z));
+  const float3 position = pos0 * bary.x + pos1 * bary.y + pos2 * bary.z;
+  g.position            = xformPoint(I.o2w, position);
+
+  float3 normal       = normalize(decompress_unit_vec(a0.w) * bary.x + decompress_unit_vec(b0.w) * bary.y + decompress_unit_vec(c0.w) * bary.z);
+  float3 worldNormal  = normalize(xformNormalT(I.w2o, normal));
+  float3 geomNormal   = normalize(cross(pos1 - pos0, pos2 - pos0));
+  float3 wgeomNormal  = normalize(xformNormalT(I.w2o, geomNormal));
+
+  const float h0 = (a1.y & 1u) ? 1.0f : -1.0f;  // handedness of vertex 0 only (shade_state.glsl:114)
+  float3 tangent = decompress_unit_vec(a1.z) * bary.x + decompress_unit_vec(b1.z) * bary.y + decompress_unit_vec(c1.z) * bary.z;
+  tangent        = normalize(tangent);
+  float3 worldTangent = normalize(xformVector(I.o2w, tangent));
+  worldTangent        = normalize(worldTangent - dot(worldTangent, worldNormal) * worldNormal);
+  g.bitangent         = cross(worldNormal, worldTangent) * h0;
+  g.tangent           = worldTangent;
+
+  const float2 uv0 = f2(__uint_as_float(a1.x), __uint_as_float(a1.y & ~1u));
+  const float2 uv1 = f2(__uint_as_float(b1.x), __uint_as_float(b1.y & ~1u));
+  const float2 uv2 = f2(__uint_as_float(c1.x), __uint_as_float(c1.y & ~1u));
+  g.texCoord       = uv0 * bary.x + uv1 * bary.y + uv2 * bary.z;
+
+  const float4 col = unpackUnorm4x8(a1.w) * bary.x + unpackUnorm4x8(b1.w) * bary.y + unpackUnorm4x8(c1.w) * bary.z;
+  g.color          = f3(col);
+  g.matIndex       = (uint32_t)max(0, geo.materialIndex);
+  g.normal         = worldNormal;
+  if(dot(g.normal, wgeomNormal) <= 0)
+    g.normal *= -1.0f;
+  return g;
+}
+
+// ---- material resolve: gltf_material.glsl:52-193 -----------------------------------------------------
+VKRT_D float4 srgbToLinear(float4 c) { return f4(pow3(f3(c), 2.2f), c.w); }
+VKRT_D float4 tex(const SceneView& sc, int id, float2 uv) { return sampleTexture(sc.textures[id], uv); }
+
+VKRT_D void resolveMaterial(const SceneView& sc, const HitGeom& g, float3 rayDir, ShadeMat& m, ShadeFrame& fr, float2& texCoord)
+{
+  const GltfShadeMaterial& mat = sc.materials[g.matIndex];
+  m.specular     = 0.5f;
+  m.subsurface   = 0.f;
+  m.specularTint = 1.f;
+
+  texCoord = applyUvTransform(mat.uvTransform, g.texCoord);
+  const float3 T0 = g.tangent, B0 = g.bitangent, N0 = g.normal;  // mat3 TBN before normal mapping
+  fr.normal    = g.normal;
+  fr.tangent   = g.tangent;
+  fr.bitangent = g.bitangent;
+  fr.ffnormal  = dot(fr.normal, rayDir) <= 0.0f ? fr.normal : -fr.normal;
+  fr.isSubsurface = false;
+
+  if(mat.normalTexture > -1)
+  {
+    float3 nv   = f3(tex(sc, mat.normalTexture, texCoord));
+    nv          = normalize(nv * 2.0f - 1.0f);
+    nv          = nv * f3(mat.normalTextureScale, mat.normalTextureScale, 1.0f);
+    fr.normal   = normalize(T0 * nv.x + B0 * nv.y + N0 * nv.z);
+    fr.ffnormal = dot(fr.normal, rayDir) <= 0.0f ? fr.normal : -fr.normal;
+    CreateCoordinateSystem(fr.ffnormal, fr.tangent, fr.bitangent);
+  }
+
+  m.emission = f3(mat.emissiveFactor[0], mat.emissiveFactor[1], mat.emissiveFactor[2]);
+  if(mat.emissiveTexture > -1)
+    m.emission *= f3(srgbToLinear(tex(sc, mat.emissiveTexture, texCoord)));
+
+  // GetMetallicRoughness
+  float dielectricSpecular = (mat.ior - 1) / (mat.ior + 1);
+  dielectricSpecular *= dielectricSpecular;
+  float perceptualRoughness = mat.pbrRoughnessFactor;
+  float metallic            = mat.pbrMetallicFactor;
+  if(mat.pbrMetallicRoughnessTexture > -1)
+  {
+    float4 mr           = tex(sc, mat.pbrMetallicRoughnessTexture, texCoord);
+    perceptualRoughness = mr.y * perceptualRoughness;
+    metallic            = mr.z * metallic;
+  }
+  float4 baseColor = f4(mat.pbrBaseColorFactor[0], mat.pbrBaseColorFactor[1], mat.pbrBaseColorFactor[2], mat.pbrBaseColorFactor[3]);
+  if(mat.pbrBaseColorTexture > -1)
+    baseColor = baseColor * srgbToLinear(tex(sc, mat.pbrBaseColorTexture, texCoord));
+  m.f0        = mix(f3(dielectricSpecular), f3(baseColor), metallic);
+  m.albedo    = f3(baseColor);
+  m.metallic  = metallic;
+  m.alpha     = baseColor.w;
+  m.roughness = fmaxf(perceptualRoughness, 0.001f);
+
+  m.transmission = mat.transmissionFactor;
+  if(mat.transmissionTexture > -1)
+    m.transmission *= tex(sc, mat.transmissionTexture, texCoord).x;
+
+  m.ior  = mat.ior;
+  fr.eta = dot(fr.normal, fr.ffnormal) > 0.0f ? (1.0f / m.ior) : m.ior;
+  m.unlit = (mat.unlit == 1);
+
+  m.anisotropy = mat.anisotropy;
+  float aspect = sqrtf(1.0f - mat.anisotropy * 0.9f);
+  m.ax         = fmaxf(0.001f, m.roughness / aspect);
+  m.ay         = fmaxf(0.001f, m.roughness * aspect);
+  if(mat.anisotropy > 0)
+  {
+    const float3 ad = f3(mat.anisotropyDirection[0], mat.anisotropyDirection[1], mat.anisotropyDirection[2]);
+    fr.tangent      = normalize(T0 * ad.x + B0 * ad.y + N0 * ad.z);
+    fr.bitangent    = normalize(cross(fr.normal, fr.tangent));
+  }
+
+  m.attenuationColor    = f3(mat.attenuationColor[0], mat.attenuationColor[1], mat.attenuationColor[2]);
+  m.attenuationDistance = mat.attenuationDistance;
+  m.thinwalled          = mat.thicknessFactor == 0;
+
+  m.clearcoat          = mat.clearcoatFactor;
+  m.clearcoatRoughness = mat.clearcoatRoughness;
+  if(mat.clearcoatTexture > -1)
+    m.clearcoat *= tex(sc, mat.clearcoatTexture, texCoord).x;
+  if(mat.clearcoatRoughnessTexture > -1)
+    m.clearcoatRoughness *= tex(sc, mat.clearcoatRoughnessTexture, texCoord).y;
+  m.clearcoatRoughness = fmaxf(m.clearcoatRoughness, 0.001f);
+
+  float4 sheen = unpackUnorm4x8(mat.sheen);
+  m.sheenTint  = f3(sheen);
+  m.sheen      = sheen.w;
+}
+
+// ---- punctual.glsl:28-51 -----------------------------------------------------------------------------
+VKRT_D float rangeAttenuation(float range, float distance)
+{
+  if(range <= 0.0f)
+    return 1.0f;
+  return fmaxf(fminf(1.0f - powf(distance / range, 4.0f), 1.0f), 0.0f) / powf(distance, 2.0f);
+}
+VKRT_D float spotAttenuation(float3 pointToLight, float3 spotDirection, float outerConeCos, float innerConeCos)
+{
+  float actualCos = dot(normalize(spotDirection), normalize(-pointToLight));
+  if(actualCos > outerConeCos)
+  {
+    if(actualCos < innerConeCos)
+      return smoothstepf(outerConeCos, innerConeCos, actualCos);
+    return 1.0f;
+  }
+  return 0.0f;
+}
+
+// ---- env_sampling.glsl:38-135 -------------------------------------------------------------------------
+VKRT_D float3 environmentSample(const SceneView& sc, float3 xi, float3& toLight, float& pdf)
+{
+  const uint32_t width = (uint32_t)sc.envW, height = (uint32_t)sc.envH;
+  const uint32_t size  = width * height;
+  const uint32_t idx   = min((uint32_t)(xi.x * (float)size), size - 1);
+  const EnvAccel sd    = sc.envAccel[idx];
+  uint32_t       envIdx;
+  if(xi.y < sd.q)
+  {
+    envIdx = idx;
+    xi.y /= sd.q;
+    pdf = sd.pdf;
+  }
+  else
+  {
+    envIdx = sd.alias;
+    xi.y   = (xi.y - sd.q) / (1.0f - sd.q);
+    pdf    = sd.aliasPdf;
+  }
+  const uint32_t px = envIdx % width;
+  const uint32_t py = envIdx / width;
+  const float    u        = (float)((float)px + xi.y) / (float)width;
+  const float    phi      = u * (2.0f * kPi) - kPi;
+  const float    sinPhi   = sinf(phi);
+  const float    cosPhi   = cosf(phi);
+  const float    stepTheta = kPi / (float)height;
+  const float    theta0    = (float)py * stepTheta;
+  const float    cosTheta  = cosf(theta0) * (1.0f - xi.z) + cosf(theta0 + stepTheta) * xi.z;
+  const float    theta     = acosf(cosTheta);
+  const float    sinTheta  = sinf(theta);
+  const float    v         = theta * kInvPi;
+  toLight = f3(cosPhi * sinTheta, cosTheta, sinPhi * sinTheta);
+  return sampleEnv(sc, f2(u, v));
+}
+
+struct ShadeOut
+{
+  bool   wantNext, wantShadow;
+  float3 nextO, nextD;
+  float3 shO, shD, shC;
+  float  shTmax;
+  uint32_t shSeed;
+};
+
+// One bounce of pathtrace.glsl:199-340 for one path.  Returns through `radiance`, `throughput`,
+// `absorption`, `seed` (all inout) and `out`.
+VKRT_D void shadeBounce(const SceneView& sc, const FrameParams& fp, float3 rayO, float3 rayD, float4 hit, float3& radiance,
+                        float3& throughput, float3& absorption, uint32_t& seed, ShadeOut& out)
+{
+  out.wantNext   = false;
+  out.wantShadow = false;
+  const int dbg      = fp.state.debugging_mode;
+  const int depth    = fp.depth;
+  const int maxDepth = fp.state.maxDepth;
+
+  // ---- miss: pathtrace.glsl:204-228 ----
+  if(hit.x == kInfinity)
+  {
+    if(dbg != VKRT_DBG_NONE)
+    {
+      if(depth != maxDepth - 1) { radiance = f3(0.f); return; }
+      if(dbg == VKRT_DBG_RADIANCE) return;
+      else if(dbg == VKRT_DBG_WEIGHT) { radiance = throughput; return; }
+      else if(dbg == VKRT_DBG_RAYDIR) { radiance = (rayD + f3(1.f)) * 0.5f; return; }
+    }
+    float3 env;
+    if(sc.sunsky.in_use == 1)
+      env = sky::sunAndSky(sc.sunsky, rayD);
+    else
+      env = sampleEnv(sc, GetSphericalUv(rayD));
+    radiance = radiance + (env * fp.state.hdrMultiplier * throughput);
+    return;
+  }
+
+  const HitGeom g = loadHitGeom(sc, __float_as_uint(hit.w), hit.y, hit.z);
+  ShadeMat   m;
+  ShadeFrame fr;
+  float2     texCoord;
+  resolveMaterial(sc, g, rayD, m, fr, texCoord);
+  m.albedo *= g.color;
+
+  // ---- debug views: pathtrace.glsl:61-83,255-256 ----
+  if(dbg != VKRT_DBG_NONE && dbg < VKRT_DBG_RADIANCE)
+  {
+    switch(dbg)
+    {
+      case VKRT_DBG_METALLIC: radiance = f3(m.metallic); break;
+      case VKRT_DBG_NORMAL: radiance = (fr.normal + f3(1.f)) * .5f; break;
+      case VKRT_DBG_BASECOLOR: radiance = m.albedo; break;
+      case VKRT_DBG_EMISSIVE: radiance = m.emission; break;
+      case VKRT_DBG_ALPHA: radiance = f3(m.alpha); break;
+      case VKRT_DBG_ROUGHNESS: radiance = f3(m.roughness); break;
+      case VKRT_DBG_TEXCOORD: radiance = f3(texCoord.x, texCoord.y, 0.f); break;
+      case VKRT_DBG_TANGENT: radiance = (fr.tangent + f3(1.f)) * .5f; break;
+      default: radiance = f3(1000.f, 0.f, 0.f); break;
+    }
+    return;
+  }
+  if(m.unlit)
+  {
+    radiance = radiance + m.albedo * throughput;
+    return;
+  }
+  if(dot(fr.normal, fr.ffnormal) > 0.0f)
+    absorption = f3(0.0f);
+  radiance += m.emission * throughput;
+  throughput *= exp3(-absorption * hit.x);
+
+  // ---- DirectLight: pathtrace.glsl:97-188 ----
+  const float3 V = -rayD;
+  float3 lightContrib, lightDir;
+  float  lightPdf;
+  float  lightDist = 1e32f;
+  bool   isLight   = false;
+  bool   visible   = false;
+  float3 vcontrib  = f3(0.f);
+  {
+    const float pSelectLight = fp.state.hdrMultiplier > 0.0f ? 0.5f : 1.0f;
+    const int   nbLights     = sc.camera.nbLights;
+    if(nbLights != 0 && rnd(seed) <= pSelectLight)
+    {
+      isLight = true;
+      int lightIndex = (int)fminf(rnd(seed) * (float)nbLights, (float)nbLights);
+      lightIndex     = min(lightIndex, nbLights - 1);  // memory safety only; unreachable for rand < 1
+      const Light& light = sc.lights[lightIndex];
+      const float3 ldir  = f3(light.direction[0], light.direction[1], light.direction[2]);
+      float3 pointToLight = -ldir;
+      float  rangeAtt = 1.0f, spotAtt = 1.0f;
+      if(light.type != VKRT_LIGHT_DIRECTIONAL)
+        pointToLight = f3(light.position[0], light.position[1], light.position[2]) - g.position;
+      lightDist = length(pointToLight);
+      if(light.type != VKRT_LIGHT_DIRECTIONAL)
+        rangeAtt = rangeAttenuation(light.range, lightDist);
+      if(light.type == VKRT_LIGHT_SPOT)
+        spotAtt = spotAttenuation(pointToLight, ldir, light.outerConeCos, light.innerConeCos);
+      lightContrib = rangeAtt * spotAtt * light.intensity * f3(light.color[0], light.color[1], light.color[2]);
+      lightDir     = normalize(pointToLight);
+      lightPdf     = 1.0f;
+    }
+    else
+    {
+      if(sc.sunsky.in_use == 1)
+      {
+        const float  sunRadius = (0.00465f * 10.0f) * sc.sunsky.sun_disk_scale;
+        const float3 sd = f3(sc.sunsky.sun_direction[0], sc.sunsky.sun_direction[1], sc.sunsky.sun_direction[2]);
+        float3 T, B;
+        CreateCoordinateSystem(sd, T, B);
+        float3 dir;
+        dir.x    = rnd(seed) * sunRadius;
+        dir.y    = rnd(seed) * sunRadius;
+        dir.z    = sqrtf(fmaxf(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
+        lightDir = normalize(T * dir.x + B * dir.y + sd * dir.z);
+        lightContrib = sky::sunAndSky(sc.sunsky, lightDir);
+        lightPdf = 0.5f;
+      }
+      else
+      {
+        float a = rnd(seed), b = rnd(seed), c = rnd(seed);
+        lightContrib = environmentSample(sc, f3(a, b, c), lightDir, lightPdf);
+      }
+      lightContrib *= fp.state.hdrMultiplier;
+    }
+    if(fr.isSubsurface || dot(lightDir, fr.ffnormal) > 0.0f)
+    {
+      float  bpdf = 0.f;
+      float3 f = (fp.state.pbrMode == 0) ? DisneyEval(m, fr, V, fr.ffnormal, lightDir, bpdf) : PbrEval(m, fr, V, fr.ffnormal, lightDir, bpdf);
+      float  misWeight = isLight ? 1.0f : fmaxf(0.0f, powerHeuristic(lightPdf, bpdf));
+      vcontrib = misWeight * f * fabsf(dot(lightDir, fr.ffnormal)) * lightContrib / lightPdf;
+      visible  = true;
+    }
+  }
+  vcontrib *= throughput;
+
+  // ---- BSDF sample: pathtrace.glsl:281-296 ----
+  float3 L   = f3(0.f);
+  float  pdf = 0.f;
+  float3 f   = (fp.state.pbrMode == 0) ? DisneySample(m, fr, V, fr.ffnormal, L, pdf, seed) : PbrSample(m, fr, V, fr.ffnormal, L, pdf, seed);
+
+  if(dot(fr.ffnormal, L) < 0.0f)
+    absorption = -log3(m.attenuationColor) / f3(m.attenuationDistance);
+
+  if(pdf > 0.0f)
+    throughput *= f * fabsf(dot(fr.ffnormal, L)) / pdf;
+  else
+    return;  // break: no shadow ray, no RR draw
+
+  if(dbg != VKRT_DBG_NONE && (depth == maxDepth - 1))
+  {
+    if(dbg == VKRT_DBG_RADIANCE) { radiance = vcontrib; return; }
+    else if(dbg == VKRT_DBG_WEIGHT) { radiance = throughput; return; }
+    else if(dbg == VKRT_DBG_RAYDIR) { radiance = (L + f3(1.f)) * 0.5f; return; }
+  }
+
+  const float rrPcont = fminf(maxcomp(throughput) * fr.eta * fr.eta + 0.001f, 0.95f);
+
+  out.nextD = L;
+  out.nextO = OffsetRay(g.position, dot(L, fr.ffnormal) > 0 ? fr.ffnormal : -fr.ffnormal);
+
+  if(visible)
+  {
+    out.wantShadow = true;
+    out.shO = out.nextO; out.shD = lightDir; out.shTmax = lightDist; out.shC = vcontrib; out.shSeed = seed;
+    // RQ: HitTest draws on prd.seed during the shadow query; RTX: the shadow payload holds a copy
+    if(sc.hasNonOpaque && fp.seedMode == VKRT_SEED_RAYQUERY)
+      pcg(seed);
+  }
+  if(rnd(seed) >= rrPcont)
+    return;
+  throughput /= rrPcont;
+  out.wantNext = (depth + 1 < maxDepth);
+}
+
+__global__ void __launch_bounds__(kShadeBlock) shadeKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
+                                                           const __grid_constant__ FrameParams fp, TraceStats* stats)
+{
+  const uint32_t count = wf.counters[0];
+  const uint32_t lane  = threadIdx.x & 31u;
+  for(uint32_t base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x)
+  {
+    const uint32_t i     = base + threadIdx.x;
+    const bool     valid = i < count;
+    ShadeOut       out;
+    out.wantNext = out.wantShadow = false;
+    uint32_t p = 0;
+    uint32_t seed = 0;
+    if(valid)
+    {
+      p = wf.queueCur[i];
+      const float4 ro = wf.rayO[p], rd = wf.rayD[p], h = wf.hit[p];
+      float4       t4 = wf.thr[p], r4 = wf.rad[p], a4 = wf.absb[p];
+      float3       throughput = f3(t4), radiance = f3(r4), absorption = f3(a4);
+      seed = __float_as_uint(t4.w);
+      if(sc.hasNonOpaque)
+        pcg(seed);  // the one draw of ClosestHit (see alphaDraw)
+      shadeBounce(sc, fp, f3(ro), f3(rd), h, radiance, throughput, absorption, seed, out);
+      wf.thr[p]  = f4(throughput, __uint_as_float(seed));
+      wf.rad[p]  = f4(radiance, 0.f);
+      wf.absb[p] = f4(absorption, 0.f);
+    }
+    // warp-aggregated queue appends (all 32 lanes reach this point)
+    const unsigned mNext = __ballot_sync(0xffffffffu, out.wantNext);
+    const unsigned mSh   = __ballot_sync(0xffffffffu, out.wantShadow);
+    uint32_t baseNext = 0, baseSh = 0;
+    if(lane == 0)
+    {
+      if(mNext) baseNext = atomicAdd(&wf.counters[1], (uint32_t)__popc(mNext));
+      if(mSh) baseSh = atomicAdd(&wf.counters[2], (uint32_t)__popc(mSh));
+    }
+    baseNext = __shfl_sync(0xffffffffu, baseNext, 0);
+    baseSh   = __shfl_sync(0xffffffffu, baseSh, 0);
+    const unsigned lt = (1u << lane) - 1u;
+    if(out.wantNext)
+    {
+      wf.queueNext[baseNext + __popc(mNext & lt)] = p;
+      wf.rayO[p] = f4(out.nextO, kInfinity);
+      wf.rayD[p] = f4(out.nextD, __uint_as_float(seed));
+    }
+    if(out.wantShadow)
+    {
+      const uint32_t k = baseSh + __popc(mSh & lt);
+      wf.shO[k] = f4(out.shO, out.shTmax);
+      wf.shD[k] = f4(out.shD, __uint_as_float(out.shSeed));
+      wf.shC[k] = f4(out.shC, __uint_as_float(p));
+    }
+  }
+  if(stats && blockIdx.x == 0 && threadIdx.x == 0)
+    atomicAdd(&stats->closestRays, (unsigned long long)count);
+}
+
+// After the shadow pass of a bounce: next -> cur, reset cursors, count shadow rays.
+__global__ void swapQueuesKernel(Wavefront wf, TraceStats* stats)
+{
+  if(stats)
+    atomicAdd(&stats->shadowRays, (unsigned long long)wf.counters[2]);
+  wf.counters[0] = wf.counters[1];
+  wf.counters[1] = 0;
+  wf.counters[2] = 0;
+  wf.counters[3] = 0;
+  wf.counters[4] = 0;
+}
+
+// ---- sample finish: firefly clamp (pathtrace.glsl:380-384) + pixel sample sum (pathtrace.comp:102-105) ---
+__global__ void __launch_bounds__(256) finishSampleKernel(const __grid_constant__ Wavefront wf, const __grid_constant__ FrameParams fp)
+{
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if(p >= wf.numPaths)
+    return;
+  float3 radiance = f3(wf.rad[p]);
+  float  lum      = dot(radiance, f3(0.212671f, 0.715160f, 0.072169f));
+  if(lum > fp.state.fireflyClampThreshold)
+    radiance *= fp.state.fireflyClampThreshold / lum;
+  float4 s  = wf.sum[p];
+  wf.sum[p] = f4(s.x + radiance.x, s.y + radiance.y, s.z + radiance.z, 0.f);
+}
+
+// ---- accumulate: pathtrace.comp:106,122-133 (running mean, frame order) ------------------------------------
+__global__ void __launch_bounds__(256) accumulateKernel(const __grid_constant__ Wavefront wf, const __grid_constant__ FrameParams fp,
+                                                        float4* __restrict__ image)
+{
+  const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
+  if(lp >= wf.numLocalPixels)
+    return;
+  const uint32_t pixel = wf.pixelOfLocal[lp];
+  float4         px    = image[pixel];
+  float3         acc   = f3(px);
+  for(int f = 0; f < fp.framesInBatch; f++)
+  {
+    const int frame      = fp.state.frame + f;
+    float3    pixelColor = f3(wf.sum[(size_t)f * wf.numLocalPixels + lp]);
+    pixelColor /= (float)fp.state.maxSamples;
+    if(frame > 0)
+      acc = mix(acc, pixelColor, 1.0f / (float)(frame + 1));
+    else
+      acc = pixelColor;
+  }
+  image[pixel] = f4(acc, 1.f);
+}
+
+// ---- tonemap: post.frag:98-147 (autoExposure off), tonemapping.glsl:24-65 -------------------------------------
+VKRT_D float3 linearTosRGB(float3 c) { return pow3(c, 1.0f / 2.2f); }
+VKRT_D float3 sRGBToLinear(float3 c) { return pow3(c, 2.2f); }
+VKRT_D float3 uncharted2Impl(float3 color)
+{
+  const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+  return ((color * (A * color + C * B) + D * E) / (color * (A * color + B) + D * F)) - E / F;
+}
+VKRT_D float3 toneMapUncharted(float3 color)
+{
+  const float W   = 11.2f;
+  color           = uncharted2Impl(color * 2.0f);
+  float3 whiteScale = f3(1.0f) / uncharted2Impl(f3(W));
+  return linearTosRGB(color * whiteScale);
+}
+__global__ void __launch_bounds__(256) tonemapKernel(const float4* __restrict__ image, int W, int H, const __grid_constant__ Tonemapper tm,
+                                                     float4* __restrict__ outF, uchar4* __restrict__ out8)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= W * H)
+    return;
+  const int x = i % W, y = i / W;
+  const float2 uvCoords = f2(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
+  const int sx = min(W - 1, max(0, (int)floorf(uvCoords.x * tm.zoom * (float)W)));
+  const int sy = min(H - 1, max(0, (int)floorf(uvCoords.y * tm.zoom * (float)H)));
+  const float4 hdr = image[(size_t)sy * W + sx];
+  float3 color = toneMapUncharted(f3(hdr) * tm.avgLum);
+  if(tm.dither > 0)
+  {
+    uint32_t rx = (uint32_t)x, ry = (uint32_t)y, rz = 0u;
+    pcg3d(rx, ry, rz);
+    const float3 noise = f3(u2f(0x3f800000u | (rx >> 9)) - 1.0f, u2f(0x3f800000u | (ry >> 9)) - 1.0f, u2f(0x3f800000u | (rz >> 9)) - 1.0f);
+    const float  quant = 1.f / 255.f;
+    const float3 lin   = sRGBToLinear(color);
+    const float3 c0    = floor3(linearTosRGB(lin) / quant) * quant;
+    const float3 c1    = c0 + quant;
+    const float3 discr = mix(sRGBToLinear(c0), sRGBToLinear(c1), noise);
+    color = f3(discr.x < lin.x ? c1.x : c0.x, discr.y < lin.y ? c1.y : c0.y, discr.z < lin.z ? c1.z : c0.z);
+  }
+  color = clamp3(mix(f3(0.5f), color, tm.contrast), 0.f, 1.f);
+  color = pow3(color, 1.0f / tm.brightness);
+  const float3 gray = f3(dot(color, f3(0.299f, 0.587f, 0.114f)));
+  color = mix(gray, color, tm.saturation);
+  const float2 uv = f2(((uvCoords.x * tm.renderingRatio[0]) - 0.5f) * 2.0f, ((uvCoords.y * tm.renderingRatio[1]) - 0.5f) * 2.0f);
+  color *= 1.0f - dot(uv, uv) * tm.vignette;
+  if(outF)
+    outF[i] = f4(color, hdr.w);
+  if(out8)
+  {
+    // UNORM8 colour attachment write: clamp, scale, round to nearest even
+    auto q = [](float f) { return (unsigned char)__float2int_rn(fminf(fmaxf(f, 0.f), 1.f) * 255.0f); };
+    out8[i] = make_uchar4(q(color.x), q(color.y), q(color.z), q(hdr.w));
+  }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------------
+void launchRaygen(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, int)
+{
+  raygenKernel<<<(wf.numPaths + 255) / 256, 256, 0, s>>>(scene, wf, fp);
+}
+void launchShade(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs)
+{
+  static int perSM = 0;
+  if(!perSM)
+  {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shadeKernel, kShadeBlock, 0);
+    if(perSM < 1) perSM = 1;
+  }
+  int grid = numSMs * perSM;
+  int need = (int)((wf.numPaths + kShadeBlock - 1) / kShadeBlock);
+  if(grid > need) grid = need;
+  if(grid < 1) grid = 1;
+  shadeKernel<<<grid, kShadeBlock, 0, s>>>(scene, wf, fp, stats);
+}
+void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats) { swapQueuesKernel<<<1, 1, 0, s>>>(wf, stats); }
+void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, int)
+{
+  finishSampleKernel<<<(wf.numPaths + 255) / 256, 256, 0, s>>>(wf, fp);
+}
+void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, int)
+{
+  accumulateKernel<<<(wf.numLocalPixels + 255) / 256, 256, 0, s>>>(wf, fp, image);
+}
+void launchTonemap(cudaStream_t s, const float4* image, int w, int h, const Tonemapper& tm, float4* outF, uchar4* out8)
+{
+  tonemapKernel<<<(w * h + 255) / 256, 256, 0, s>>>(image, w, h, tm, outF, out8);
+}
+
+}  // namespace vkrt

@@ -1,0 +1,73 @@
+"""Loader for libvkrt_b200.so.  Fails loudly when the CUDA library has not been built:
+there is no CPU or PyTorch fallback for the product path."""
+import ctypes as C
+import os
+
+from . import structs as S
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(_HERE, "libvkrt_b200.so")
+
+
+# every symbol include/vkrt_b200.h declares
+EXPORTS = [
+    "vkrt_create", "vkrt_destroy", "vkrt_name", "vkrt_last_error", "vkrt_scene_begin", "vkrt_scene_add_primmesh",
+    "vkrt_scene_add_node", "vkrt_scene_set_materials", "vkrt_scene_set_lights", "vkrt_scene_add_texture", "vkrt_scene_commit",
+    "vkrt_build_env_accel", "vkrt_set_environment", "vkrt_set_sunsky", "vkrt_set_camera", "vkrt_output_create",
+    "vkrt_output_device_ptr", "vkrt_output_clear", "vkrt_output_read", "vkrt_tonemap", "vkrt_tonemap_float", "vkrt_render",
+    "vkrt_sync", "vkrt_pack_vertices", "vkrt_make_camera", "vkrt_light_from_matrix", "vkrt_trace_rays", "vkrt_triangle_ids",
+    "vkrt_get_stats", "vkrt_reset_stats",
+]
+
+
+def load_library():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise LibraryMissing(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(path)
+    vp, u32, i32, f32p = C.c_void_p, C.c_uint32, C.c_int32, C.POINTER(C.c_float)
+    lib.vkrt_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.vkrt_destroy.argtypes = [vp]
+    lib.vkrt_name.restype = C.c_char_p
+    lib.vkrt_last_error.argtypes = [vp]
+    lib.vkrt_last_error.restype = C.c_char_p
+    lib.vkrt_scene_begin.argtypes = [vp]
+    lib.vkrt_scene_add_primmesh.argtypes = [vp, vp, u32, vp, u32, i32]
+    lib.vkrt_scene_add_node.argtypes = [vp, vp, u32]
+    lib.vkrt_scene_set_materials.argtypes = [vp, vp, u32]
+    lib.vkrt_scene_set_lights.argtypes = [vp, vp, u32]
+    lib.vkrt_scene_add_texture.argtypes = [vp, vp, u32, u32, i32, i32, i32, i32]
+    lib.vkrt_scene_commit.argtypes = [vp, i32]
+    lib.vkrt_build_env_accel.argtypes = [vp, u32, u32, vp, f32p, f32p]
+    lib.vkrt_set_environment.argtypes = [vp, vp, u32, u32, vp]
+    lib.vkrt_set_sunsky.argtypes = [vp, C.POINTER(S.SunAndSky)]
+    lib.vkrt_set_camera.argtypes = [vp, C.POINTER(S.SceneCamera)]
+    lib.vkrt_output_create.argtypes = [vp, u32, u32, vp]
+    lib.vkrt_output_device_ptr.argtypes = [vp, C.POINTER(vp)]
+    lib.vkrt_output_clear.argtypes = [vp]
+    lib.vkrt_output_read.argtypes = [vp, vp]
+    lib.vkrt_tonemap.argtypes = [vp, C.POINTER(S.Tonemapper), vp]
+    lib.vkrt_tonemap_float.argtypes = [vp, C.POINTER(S.Tonemapper), vp]
+    lib.vkrt_render.argtypes = [vp, C.POINTER(S.RtxState), i32, C.POINTER(S.RenderOpts)]
+    lib.vkrt_sync.argtypes = [vp]
+    lib.vkrt_pack_vertices.argtypes = [vp, vp, vp, vp, vp, u32, vp]
+    lib.vkrt_make_camera.argtypes = [vp, vp, vp, C.c_float, C.c_float, C.c_float, i32, C.POINTER(S.SceneCamera)]
+    lib.vkrt_light_from_matrix.argtypes = [vp, vp]
+    lib.vkrt_trace_rays.argtypes = [vp, vp, u32, i32, vp]
+    lib.vkrt_triangle_ids.argtypes = [vp, vp, u32, vp]
+    lib.vkrt_get_stats.argtypes = [vp, C.POINTER(S.Stats)]
+    lib.vkrt_reset_stats.argtypes = [vp]
+    _LIB = lib
+    return lib
