@@ -60,8 +60,8 @@ typedef struct vkrt_stats
 {
   uint64_t closest_rays;    /* ClosestHit() calls (shaders/traceray_rq.glsl:108)  */
   uint64_t shadow_rays;     /* AnyHit() calls     (shaders/traceray_rq.glsl:153)  */
-  uint64_t nodes_visited;   /* BVH2 nodes fetched (instrumented kernels only)     */
-  uint64_t tris_tested;     /* triangles fetched  (instrumented kernels only)     */
+  uint64_t nodes_visited;   /* BVH2 nodes fetched by both trace kernels (instrumented kernels only) */
+  uint64_t tris_tested;     /* triangles fetched by both trace kernels (instrumented kernels only)  */
   uint64_t frames_rendered; /* frames since the last vkrt_reset_stats             */
   uint64_t kernel_launches; /* kernels of this library launched                   */
   double   ms_raygen;       /* device time per kernel family, CUDA events, summed */
@@ -76,7 +76,11 @@ typedef struct vkrt_stats
   uint32_t num_bvh_nodes;   /* 64-byte BVH2 nodes                                 */
   uint32_t num_instances;   /* TLAS-equivalent nodes (src/accelstruct.cpp:132)    */
   uint32_t has_non_opaque;  /* any instance that is not FORCE_OPAQUE              */
-  double   reserved[8];
+  uint64_t shadow_nodes_visited; /* the any-hit kernel's share of nodes_visited   */
+  uint64_t shadow_tris_tested;   /* the any-hit kernel's share of tris_tested     */
+  uint32_t bvh_max_depth;   /* depth of the BVH2 (traversal stack bound)          */
+  uint32_t _pad;
+  double   reserved[5];
 } vkrt_stats;
 
 /* ---- context ---------------------------------------------------------- */
@@ -177,6 +181,11 @@ int vkrt_light_from_matrix(const float world_matrix[16], Light* inout_light);
 int vkrt_trace_rays(vkrt_ctx* ctx, const float* rays, uint32_t n, int32_t closest, float* out_hits);
 /* For a flattened triangle id returned above: {node(instance) index, primitive index}. */
 int vkrt_triangle_ids(vkrt_ctx* ctx, const uint32_t* tri_ids, uint32_t n, uint32_t* out_node_prim);
+
+/* Device-side stopwatch on the context stream (CUDA events): mark(0) .. mark(1), then
+ * elapsed_ms() synchronises and returns the time between the two marks. */
+int vkrt_mark(vkrt_ctx* ctx, int32_t which);
+int vkrt_elapsed_ms(vkrt_ctx* ctx, float* out_ms);
 
 int vkrt_get_stats(vkrt_ctx* ctx, vkrt_stats* out);
 int vkrt_reset_stats(vkrt_ctx* ctx);

@@ -46,6 +46,7 @@ def load():
         L.oracle_output_read.argtypes = [vp, vp]
         L.oracle_output_write.argtypes = [vp, vp]
         L.oracle_render.argtypes = [vp, vp, i32, i32, i32, i32]
+        L.oracle_render_tiles.argtypes = [vp, vp, i32, i32, i32, i32, i32]
         L.oracle_tonemap.argtypes = [vp, vp, vp, vp]
         L.oracle_trace_rays.argtypes = [vp, vp, u32, i32, vp]
         L.oracle_triangle_ids.argtypes = [vp, vp, u32, vp]
@@ -178,6 +179,9 @@ class Oracle:
 
     def render(self, state, num_frames=1, seed_mode=0, rows=(0, 0)):
         self._ck(self.lib.oracle_render(self.h, C.byref(state), num_frames, seed_mode, rows[0], rows[1]), "render")
+
+    def render_tiles(self, state, num_frames=1, seed_mode=0, tile=64, shard_rank=0, shard_count=1):
+        self._ck(self.lib.oracle_render_tiles(self.h, C.byref(state), num_frames, seed_mode, tile, shard_rank, shard_count), "render_tiles")
 
     def tonemap(self, tm):
         out = np.empty((self.height, self.width, 4), dtype=np.uint8)

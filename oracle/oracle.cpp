@@ -281,6 +281,51 @@ int oracle_output_write(OracleCtx* c, const float* in)
   return 0;
 }
 
+// Tile-sharded variant (mirrors vkrt_render_opts.tile_size/shard_rank/shard_count): only pixels of tiles t with
+// t % shard_count == shard_rank are rendered; everything else is left untouched.
+int oracle_render_tiles(OracleCtx* c, const RtxState* state, int32_t num_frames, int32_t seed_mode, int32_t tile, int32_t shard_rank, int32_t shard_count)
+{
+  if(!c->committed || c->scene.envW == 0)
+    return 3;
+  const int W = state->size[0], H = state->size[1];
+  if(W != c->width || H != c->height || tile <= 0 || shard_count <= 0)
+    return 1;
+  const int tx = (W + tile - 1) / tile;
+  int nt = c->threads > 0 ? c->threads : (int)std::thread::hardware_concurrency();
+  if(nt < 1) nt = 1;
+  for(int f = 0; f < num_frames; f++)
+  {
+    RtxState st = *state;
+    st.frame    = state->frame + f;
+    std::atomic<int> next{0};
+    std::mutex       mtx;
+    auto work = [&]() {
+      RenderCounters local;
+      for(;;)
+      {
+        int y = next.fetch_add(1);
+        if(y >= H)
+          break;
+        for(int x = 0; x < W; x++)
+        {
+          int t = (y / tile) * tx + (x / tile);
+          if(t % shard_count == shard_rank)
+            renderPixel(c->scene, st, seed_mode, x, y, c->image.data(), &local);
+        }
+      }
+      std::lock_guard<std::mutex> g(mtx);
+      c->counters.closestRays += local.closestRays;
+      c->counters.shadowRays += local.shadowRays;
+      c->counters.trace.nodes += local.trace.nodes;
+      c->counters.trace.tris += local.trace.tris;
+    };
+    std::vector<std::thread> th;
+    for(int t = 0; t < nt; t++) th.emplace_back(work);
+    for(auto& t : th) t.join();
+  }
+  return 0;
+}
+
 // Renders frames state->frame .. +num_frames-1 over rows [row_begin,row_end) (0,0 = all).
 int oracle_render(OracleCtx* c, const RtxState* state, int32_t num_frames, int32_t seed_mode, int32_t row_begin, int32_t row_end)
 {

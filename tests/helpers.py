@@ -1,0 +1,49 @@
+"""Shared test helpers: small deterministic scenes and ray sets."""
+import numpy as np
+
+from vk_raytrace_b200 import scenes, structs as S
+from vk_raytrace_b200.context import MeshDesc, SceneDesc
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.sqrt(((a - b) ** 2).sum() / max((b ** 2).sum(), 1e-300)))
+
+
+def random_rays(n, seed, extent=3.0, tmax=1e32, centre=(0, 0, 0)):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(-extent, extent, (n, 3)) + np.asarray(centre)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros((n, 8), dtype=np.float32)
+    rays[:, :3] = o
+    rays[:, 3] = tmax
+    rays[:, 4:7] = d
+    rays[:, 7] = rng.integers(0, 2 ** 32, n, dtype=np.uint32).view(np.float32)
+    return rays
+
+
+def small_sponza():
+    return scenes.sponza_standin(detail=0.03, tex_size=64, env_size=(64, 32))
+
+
+def triangle_soup(n, seed, double_sided=False, mirrored=False):
+    """n random triangles in one primMesh; optionally instanced through a mirroring (det < 0) matrix."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-2, 2, (n, 1, 3))
+    p = (c + rng.normal(scale=0.35, size=(n, 3, 3))).reshape(-1, 3).astype(np.float32)
+    mesh = scenes.finish_mesh(p, np.arange(3 * n, dtype=np.uint32), None, 0, smooth=False)
+    s = SceneDesc(name="soup")
+    s.meshes = [mesh]
+    m = np.eye(4, dtype=np.float32)
+    if mirrored:
+        m = scenes.scale(-1.0, 1.0, 1.0) @ scenes.rotate((0, 1, 0), 0.3)
+    s.nodes = [(m, 0), (scenes.translate(0.5, 0.25, -0.5) @ scenes.rotate((1, 1, 0), 1.1) @ m, 0)]
+    mats = S.default_material(1)
+    mats["pbrMetallicFactor"] = 0.0
+    mats["doubleSided"] = 1 if double_sided else 0
+    s.materials = mats
+    s.env = scenes.constant_environment(8, 4, 1.0)
+    s.camera = dict(eye=(0, 0, 6), center=(0, 0, 0), up=(0, 1, 0), fov=45.0)
+    return s

@@ -1,0 +1,123 @@
+"""CPU tests of the drop-in boundary: the C ABI loads and exports every declared symbol, struct layouts match
+the reference, and the host-side halves (vertex packing, alias table, camera) agree with the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import small_sponza
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported(vk):
+    hdr = open(os.path.join(ROOT, "include", "vkrt_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(vkrt_[a-z0-9_]+)\s*\(", hdr)))
+    from vk_raytrace_b200.lib import EXPORTS
+    assert declared and set(declared) == set(EXPORTS), (set(declared) ^ set(EXPORTS))
+    lib = vk.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_struct_sizes_match_reference_layout(vk):
+    from vk_raytrace_b200 import structs as S
+    assert C.sizeof(S.SceneCamera) == 140
+    assert C.sizeof(S.RtxState) == 48
+    assert C.sizeof(S.Tonemapper) == 48
+    assert C.sizeof(S.SunAndSky) == 96
+    assert S.VertexAttributes.itemsize == 32
+    assert S.GltfShadeMaterial.itemsize == 216
+    assert S.Light.itemsize == 64
+    assert S.EnvAccel.itemsize == 16
+    # C side: the header static_asserts the same numbers; compile it as plain C
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "t.c")
+        open(src, "w").write('#include "vkrt_b200.h"\nint main(void){return (int)sizeof(vkrt_stats) - 192;}\n')
+        subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), src, "-o", os.path.join(d, "t")])
+        assert subprocess.call([os.path.join(d, "t")]) == 0
+
+
+def test_create_fails_loudly_without_gpu(vk):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = vk.load_library()
+    h = C.c_void_p()
+    rc = lib.vkrt_create(0, C.byref(h))
+    assert rc != 0 and not h.value   # no CPU fallback
+    with pytest.raises(RuntimeError):
+        vk.Context(0)
+
+
+def test_vertex_packing_matches_oracle_bit_for_bit(vk, ob):
+    from vk_raytrace_b200.context import pack_vertices
+    sc = small_sponza()
+    for m in sc.meshes[:12]:
+        a, b = pack_vertices(m), ob.pack_vertices(m)
+        assert a.tobytes() == b.tobytes()
+    # handedness bit and special values
+    from vk_raytrace_b200.context import MeshDesc
+    n = 6
+    m = MeshDesc(np.zeros((n, 3), np.float32), np.array([[0, 0, 1], [0, 0, -1], [1, 0, 0], [0, -1, 0], [.5, .5, -.7071], [np.inf, 0, 0]], np.float32),
+                 np.array([[1, 0, 0, 1], [1, 0, 0, -1], [0, 1, 0, 1], [0, 0, 1, -1], [0, 1, 0, 1], [0, 1, 0, -1]], np.float32),
+                 np.array([[0.25, 0.75]] * n, np.float32), np.array([[0, 0.5, 1, 1.5]] * n, np.float32), np.arange(6, dtype=np.uint32), 0)
+    a, b = pack_vertices(m), ob.pack_vertices(m)
+    assert a.tobytes() == b.tobytes()
+    assert (a["texcoord"][:, 1].view(np.uint32) & 1).tolist() == [1, 0, 1, 0, 1, 0]
+    assert a["normal"][5] == 0xFFFFFFFF and a["color"][0] == 0xFFFF8000
+
+
+def test_alias_table_matches_oracle_bit_for_bit(vk, ob):
+    from vk_raytrace_b200 import scenes
+    from vk_raytrace_b200.context import build_env_accel
+    for env in (scenes.sky_environment(64, 32, 3), scenes.constant_environment(16, 8, 1.0), scenes.sky_environment(128, 64, 11, sun_power=5000.0)):
+        a, ia, aa = build_env_accel(env)
+        b, ib, ab = ob.build_env_accel(env)
+        assert a.tobytes() == b.tobytes() and ia == ib and aa == ab
+
+
+def test_alias_table_invariants(vk):
+    """Walker alias table: every texel's total selection probability equals importance / sum (src/hdr_sampling.cpp:107-176)."""
+    from vk_raytrace_b200 import scenes
+    from vk_raytrace_b200.context import build_env_accel
+    env = scenes.sky_environment(64, 32, 5)
+    acc, integral, avg = build_env_accel(env)
+    h, w = env.shape[:2]
+    n = h * w
+    assert acc["alias"].max() < n
+    q = np.clip(acc["q"].astype(np.float64), 0, 1)
+    prob = q / n
+    np.add.at(prob, acc["alias"], (1 - q) / n)
+    theta = (np.arange(h + 1)) * np.pi / h
+    area = (np.cos(theta[:-1]) - np.cos(theta[1:])) * (2 * np.pi / w)
+    imp = (env[..., :3].max(axis=2) * area[:, None]).reshape(-1).astype(np.float64)
+    want = imp / imp.sum()
+    assert abs(imp.sum() - integral) / integral < 1e-4
+    # (the construction stops with a few above-average texels left at q > 1, which the sampler treats as q = 1:
+    #  the reference's table is exact up to that residue)
+    assert np.all(np.abs(prob - want) <= 2e-2 * want + 1e-9) and np.median(np.abs(prob - want) / want) < 1e-4 and abs(prob.sum() - 1) < 1e-3
+    # pdf = max(rgb) / integral, aliasPdf = pdf[alias]
+    assert np.allclose(acc["pdf"], env[..., :3].max(axis=2).reshape(-1) / integral, rtol=1e-6)
+    assert np.array_equal(acc["aliasPdf"], acc["pdf"][acc["alias"]])
+    assert abs(avg - (env[..., 0] * 0.2126 + env[..., 1] * 0.7152 + env[..., 2] * 0.0722).mean()) < 1e-4 * avg
+
+
+def test_make_camera(vk):
+    from vk_raytrace_b200.context import make_camera
+    cam = make_camera((1, 2, 5), (0, 0.5, 0), (0, 1, 0), 45.0, 16 / 9, 0.1, 3)
+    vi = np.array(cam.viewInverse, dtype=np.float64).reshape(4, 4).T   # column-major -> math
+    pi = np.array(cam.projInverse, dtype=np.float64).reshape(4, 4).T
+    assert np.allclose(vi[:3, 3], (1, 2, 5), atol=1e-5)                 # viewInverse * (0,0,0,1) = eye
+    fwd = -vi[:3, 2]
+    want = np.array([0, 0.5, 0]) - np.array([1, 2, 5])
+    assert np.allclose(fwd, want / np.linalg.norm(want), atol=1e-5)
+    assert abs(cam.focalDist - np.linalg.norm(want)) < 1e-5 and cam.nbLights == 3 and abs(cam.aperture - 0.1) < 1e-7
+    # projInverse maps NDC (0,0,1) onto the -Z axis and y is flipped (proj[1][1] *= -1)
+    t = pi @ np.array([0, 0, 1, 1.0])
+    assert abs(t[0]) < 1e-6 and abs(t[1]) < 1e-6 and t[2] / t[3] < 0
+    up = pi @ np.array([0, -1, 1, 1.0])
+    assert up[1] / abs(up[2]) > 0 and abs(up[1] / -up[2] - np.tan(np.radians(45.0) / 2)) < 1e-5

@@ -1,0 +1,271 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA wavefront path, called through the C ABI, against the CPU
+oracle on the same seeded inputs, against the committed golden fixtures, and -- at BASELINE.json's full size -- through
+size-independent properties (determinism, batching invariance, shard-union == whole).
+
+Tolerances: traversal results (t, u, v, triangle id) and integer pieces are bit-exact.  Images are floating point:
+BASELINE.json's north_star allows 1e-3 relative per-channel L2; CUDA and glibc transcendentals differ by ulps, so
+measured values sit around 1e-7..1e-5 and the tests assert 1e-4 (images) with a per-pixel outlier budget."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import random_rays, rel_l2, small_sponza, triangle_soup
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+IMG_TOL = 1e-4      # relative L2 per channel (north_star allows 1e-3)
+
+
+def per_channel_rel_l2(a, b):
+    return max(rel_l2(a[..., c], b[..., c]) for c in range(3))
+
+
+def both(vk, ob, gpu, scene, W, H, build_mode=0):
+    o = ob.Oracle()
+    vk.upload_scene(gpu, scene, W, H, build_mode=build_mode)
+    vk.upload_scene(o, scene, W, H)
+    return o
+
+
+# ---------------------------------------------------------------------------------------------- traversal
+@pytest.mark.parametrize("which,build_mode", [("cornell", 0), ("sponza", 0), ("sponza", 1), ("soup", 0), ("soup_mirrored_double", 1)])
+def test_trace_rays_bit_exact(vk, ob, gpu, which, build_mode):
+    from vk_raytrace_b200 import scenes
+    sc = {"cornell": lambda: scenes.cornell_box(), "sponza": small_sponza, "soup": lambda: triangle_soup(500, 1),
+          "soup_mirrored_double": lambda: triangle_soup(500, 2, double_sided=True, mirrored=True)}[which]()
+    o = both(vk, ob, gpu, sc, 16, 16, build_mode)
+    n = 20000
+    rays = random_rays(n, 11, 14.0 if which == "sponza" else 3.0, centre=(0, 3, 0) if which == "sponza" else (0, 0, 0))
+    rays[: n // 4, 3] = 2.5
+    for closest in (True, False):
+        a, b = gpu.trace_rays(rays, closest), o.trace_rays(rays, closest)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    hit = b[:, 0] < 1e31
+    assert hit.sum() > n // 20
+    # flattened triangle id -> (node, primitive) mapping agrees too
+    ids = gpu.trace_rays(rays, True)[:, 3].view(np.uint32)[gpu.trace_rays(rays, True)[:, 0] < 1e31][:512]
+    assert np.array_equal(gpu.triangle_ids(ids), o.triangle_ids(ids))
+
+
+def test_trace_matches_golden_probe(vk, gpu):
+    from vk_raytrace_b200 import scenes
+    g = np.load(os.path.join(G, "cornell64.npz"))
+    vk.upload_scene(gpu, scenes.cornell_box(with_light=True), 64, 64)
+    assert np.array_equal(gpu.trace_rays(g["probe_rays"], True).view(np.uint32), g["probe_hits_closest"].view(np.uint32))
+    assert np.array_equal(gpu.trace_rays(g["probe_rays"], False).view(np.uint32), g["probe_hits_any"].view(np.uint32))
+
+
+def test_degenerate_scenes(vk, ob, gpu):
+    """Edge cases: empty scene (no nodes), a single triangle, degenerate (zero-area) triangles, rays with zero direction components."""
+    from vk_raytrace_b200 import scenes, structs as S
+    from vk_raytrace_b200.context import SceneDesc
+    empty = SceneDesc()
+    empty.materials = S.default_material(1)
+    empty.env = scenes.constant_environment(8, 4, 0.5)
+    empty.camera = dict(eye=(0, 0, 3), center=(0, 0, 0), up=(0, 1, 0), fov=45.0)
+    o = both(vk, ob, gpu, empty, 16, 8)
+    rays = random_rays(256, 1)
+    assert np.array_equal(gpu.trace_rays(rays).view(np.uint32), o.trace_rays(rays).view(np.uint32))
+    st = S.default_rtx_state(16, 8, maxDepth=3)
+    gpu.render(st, 1)
+    o.render(st, 1)
+    assert np.allclose(gpu.output_read(), o.output_read(), rtol=1e-6) and np.allclose(gpu.output_read()[..., :3], 0.5)
+    one = SceneDesc()
+    pos = np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0], [2, 2, 2], [2, 2, 2], [2, 2, 2]], np.float32)   # second triangle is degenerate
+    one.meshes = [scenes.finish_mesh(pos, [0, 1, 2, 3, 4, 5], None, 0, smooth=False)]
+    one.nodes = [(np.eye(4, dtype=np.float32), 0)]
+    one.materials, one.env, one.camera = empty.materials, empty.env, empty.camera
+    o = both(vk, ob, gpu, one, 16, 8)
+    rays = random_rays(4096, 2, 1.5)
+    rays[:64, 4:7] = (0, 0, -1)        # axis aligned: zero components
+    rays[:64, 2] = 2.0
+    assert np.array_equal(gpu.trace_rays(rays).view(np.uint32), o.trace_rays(rays).view(np.uint32))
+    assert (gpu.trace_rays(rays)[:, 0] < 1e31).sum() > 10
+
+
+# ---------------------------------------------------------------------------------------------- images
+@pytest.mark.parametrize("pbr", [0, 1])
+def test_cornell_matches_oracle_and_golden(vk, ob, gpu, pbr):
+    from vk_raytrace_b200 import scenes, structs as S
+    g = np.load(os.path.join(G, "cornell64.npz"))
+    W = H = 64
+    o = both(vk, ob, gpu, scenes.cornell_box(with_light=True), W, H)
+    st = S.default_rtx_state(W, H, maxDepth=4, pbrMode=pbr)
+    gpu.reset_stats()
+    gpu.render(st, 4)
+    o.render(st, 4)
+    a, b = gpu.output_read(), o.output_read()
+    assert per_channel_rel_l2(a[..., :3], b[..., :3]) < IMG_TOL
+    assert per_channel_rel_l2(a[..., :3], g[f"radiance_pbr{pbr}"]) < IMG_TOL
+    assert np.all(a[..., 3] == 1.0)
+    # opaque scene: the two implementations trace exactly the same rays
+    s, c = gpu.stats(), o.counters()
+    assert (s.closest_rays, s.shadow_rays) == (c["closest_rays"], c["shadow_rays"])
+
+
+@pytest.mark.parametrize("dbg", list(range(1, 12)))
+def test_debug_views(vk, ob, gpu, dbg):
+    """C1 of BASELINE.json: every DebugMode (shaders/host_device.h:88-102) at depth 1 (9-11: depth 3)."""
+    from vk_raytrace_b200 import scenes, structs as S
+    g = np.load(os.path.join(G, "cornell64.npz"))
+    W = H = 64
+    vk.upload_scene(gpu, scenes.cornell_box(with_light=True), W, H)
+    st = S.default_rtx_state(W, H, maxDepth=1 if dbg < 9 else 3, debugging_mode=dbg)
+    gpu.render(st, 1)
+    a = gpu.output_read()[..., :3]
+    want = g[f"debug{dbg}"]
+    assert np.abs(a - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("pbr,seed_mode", [(0, 0), (1, 0), (0, 1)])
+def test_sponza_with_alpha_textures_lights(vk, ob, gpu, pbr, seed_mode):
+    """Textured scene with MASK-alpha drapes, punctual + spot lights, normal maps, transmission, clearcoat, anisotropy."""
+    from vk_raytrace_b200 import structs as S
+    W, H = 96, 64
+    o = both(vk, ob, gpu, small_sponza(), W, H)
+    assert gpu.stats().has_non_opaque == 1
+    st = S.default_rtx_state(W, H, maxDepth=6, pbrMode=pbr)
+    opts = S.RenderOpts()
+    opts.seed_mode = seed_mode
+    gpu.render(st, 4, opts)
+    o.render(st, 4, seed_mode=seed_mode)
+    a, b = gpu.output_read()[..., :3], o.output_read()[..., :3]
+    assert np.isfinite(a).all()
+    # a few pixels may take a different branch because of ulp differences in sin/cos/pow: bounded count, bounded L2
+    off = (np.abs(a - b) > 1e-3 * (1 + np.abs(b))).any(axis=2).sum()
+    assert off <= 0.005 * W * H, off
+    assert per_channel_rel_l2(a, b) < 1e-3
+
+
+def test_multi_sample_frames_and_clamp(vk, ob, gpu):
+    """maxSamples > 1 (the RNG stream continues across samples, pathtrace.comp:101-106) and the firefly clamp."""
+    from vk_raytrace_b200 import scenes, structs as S
+    W = H = 48
+    o = both(vk, ob, gpu, scenes.cornell_box(with_light=True), W, H)
+    st = S.default_rtx_state(W, H, maxDepth=4, maxSamples=3, fireflyClampThreshold=0.4, frame=2)
+    gpu.output_clear()
+    gpu.render(st, 2)
+    o.render(st, 2)
+    assert per_channel_rel_l2(gpu.output_read()[..., :3], o.output_read()[..., :3]) < IMG_TOL
+
+
+def test_sun_and_sky_environment(vk, ob, gpu):
+    from vk_raytrace_b200 import scenes, structs as S
+    W, H = 64, 40
+    sc = scenes.cornell_box()
+    sc.nodes = sc.nodes[:1] + sc.nodes[6:]     # floor + the two boxes under an open sky
+    o = both(vk, ob, gpu, sc, W, H)
+    ss = S.default_sunsky(in_use=1)
+    gpu.set_sunsky(ss)
+    o.set_sunsky(ss)
+    st = S.default_rtx_state(W, H, maxDepth=4)
+    gpu.render(st, 3)
+    o.render(st, 3)
+    a, b = gpu.output_read()[..., :3], o.output_read()[..., :3]
+    assert a.max() > 0 and per_channel_rel_l2(a, b) < 1e-3
+    gpu.set_sunsky(S.default_sunsky())
+
+
+def test_tonemap(vk, ob, gpu):
+    from vk_raytrace_b200 import scenes, structs as S
+    g = np.load(os.path.join(G, "cornell64.npz"))
+    W = H = 64
+    o = both(vk, ob, gpu, scenes.cornell_box(with_light=True), W, H)
+    st = S.default_rtx_state(W, H, maxDepth=4)
+    gpu.render(st, 4)
+    o.render(st, 4)
+    for tm in (S.default_tonemapper(), S.default_tonemapper(dither=0, contrast=1.2, brightness=0.8, saturation=0.5, vignette=0.3, avgLum=1.7)):
+        a8, b8 = gpu.tonemap(tm).astype(int), o.tonemap(tm).astype(int)
+        assert np.abs(a8 - b8).max() <= 1 and (a8 != b8).mean() < 0.01
+        af, bf = gpu.tonemap_float(tm), o.tonemap_float(tm)
+        assert np.abs(af - bf).max() < 5e-3 and rel_l2(af, bf) < 1e-3      # dithering quantises: a flipped step is 1/255
+    a8 = gpu.tonemap(S.default_tonemapper()).astype(int)
+    assert np.abs(a8 - g["tonemapped_rgba8"].astype(int)).max() <= 1
+
+
+# ---------------------------------------------------------------------------------------------- invariances
+def test_batching_and_sharding_do_not_change_the_image(vk, gpu):
+    """frames_in_flight only changes scheduling; tile shards of N contexts sum to the whole image (bit-exact)."""
+    from vk_raytrace_b200 import structs as S
+    W, H = 200, 120
+    vk.upload_scene(gpu, small_sponza(), W, H)
+    st = S.default_rtx_state(W, H, maxDepth=5)
+    imgs = []
+    for fif in (1, 3, 8):
+        opts = S.RenderOpts()
+        opts.frames_in_flight = fif
+        gpu.output_clear()
+        gpu.render(st, 6, opts)
+        imgs.append(gpu.output_read())
+    assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
+    total = np.zeros_like(imgs[0])
+    for rank in range(3):
+        opts = S.RenderOpts()
+        opts.shard_rank, opts.shard_count, opts.tile_size = rank, 3, 32
+        gpu.output_clear()
+        gpu.render(st, 6, opts)
+        part = gpu.output_read()
+        assert (part[..., 3] == 1).sum() > 0.2 * W * H
+        total += part
+    assert np.array_equal(total, imgs[0])
+    # frame-by-frame calls == one multi-frame call
+    gpu.output_clear()
+    for f in range(6):
+        st1 = S.default_rtx_state(W, H, maxDepth=5, frame=f)
+        gpu.render(st1, 1)
+    assert np.array_equal(gpu.output_read(), imgs[0])
+
+
+def test_external_output_buffer_and_errors(vk, gpu):
+    import torch
+    from vk_raytrace_b200 import scenes, structs as S
+    W = H = 32
+    vk.upload_scene(gpu, scenes.cornell_box(), W, H)
+    st = S.default_rtx_state(W, H, maxDepth=2)
+    gpu.render(st, 1)
+    want = gpu.output_read()
+    buf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda:0")
+    gpu.output_create(W, H, buf.data_ptr())
+    assert gpu.output_device_ptr() == buf.data_ptr()
+    gpu.render(st, 1)
+    assert np.array_equal(buf.cpu().numpy(), want)
+    gpu.output_create(W, H)
+    bad = S.default_rtx_state(W + 1, H)
+    with pytest.raises(RuntimeError):
+        gpu.render(bad, 1)
+    with pytest.raises(RuntimeError):
+        gpu.render(S.default_rtx_state(W, H, debugging_mode=12), 1)
+
+
+@pytest.mark.parametrize("build_mode", [0, 1])
+def test_full_size_properties_sponza_1080p(vk, gpu, build_mode):
+    """BASELINE.json configs[2] at full size (262k triangles, 1920x1080, depth 8): determinism, batching invariance,
+    ray accounting, and agreement of sampled pixels with the oracle (the oracle only renders a band of rows)."""
+    from oracle import binding as ob
+    from vk_raytrace_b200 import scenes, structs as S
+    W, H = 1920, 1080
+    sc = scenes.sponza_standin(detail=1.0, tex_size=256, env_size=(512, 256))
+    vk.upload_scene(gpu, sc, W, H, build_mode=build_mode)
+    s = gpu.stats()
+    assert 240_000 < s.num_triangles < 290_000 and s.bvh_max_depth < 128
+    st = S.default_rtx_state(W, H, maxDepth=8)
+    gpu.reset_stats()
+    gpu.render(st, 3)
+    a = gpu.output_read()
+    s1 = gpu.stats()
+    opts = S.RenderOpts()
+    opts.frames_in_flight = 1
+    gpu.output_clear()
+    gpu.render(st, 3, opts)
+    b = gpu.output_read()
+    assert np.array_equal(a, b) and np.isfinite(a).all()
+    assert 3 * W * H <= s1.closest_rays <= 3 * W * H * 8 and s1.shadow_rays <= s1.closest_rays
+    o = ob.Oracle()
+    vk.upload_scene(o, sc, W, H)
+    rows = (500, 508)
+    o.render(st, 3, rows=rows)
+    ref = o.output_read()[rows[0]:rows[1], :, :3]
+    got = a[rows[0]:rows[1], :, :3]
+    off = (np.abs(got - ref) > 1e-3 * (1 + np.abs(ref))).any(axis=2).mean()
+    assert off < 0.005 and per_channel_rel_l2(got, ref) < 1e-3

@@ -211,6 +211,14 @@ class Context:
         self._ck(self.lib.vkrt_triangle_ids(self.h, _ptr(ids), len(ids), _ptr(out)), "triangle_ids")
         return out
 
+    def mark(self, which):
+        self._ck(self.lib.vkrt_mark(self.h, which), "mark")
+
+    def elapsed_ms(self):
+        ms = C.c_float()
+        self._ck(self.lib.vkrt_elapsed_ms(self.h, C.byref(ms)), "elapsed_ms")
+        return ms.value
+
     def stats(self):
         s = S.Stats()
         self._ck(self.lib.vkrt_get_stats(self.h, C.byref(s)), "get_stats")

@@ -89,6 +89,7 @@ struct vkrt_ctx
   vkrt_stats  stats{};
   struct Timed { cudaEvent_t a, b; int slot; };
   std::vector<Timed>       pending;
+  cudaEvent_t              marks[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> eventPool;
 };
 
@@ -245,6 +246,7 @@ int vkrt_destroy(vkrt_ctx* ctx)
   cudaStreamSynchronize(ctx->stream);
   drainTimers(ctx);
   for(auto e : ctx->eventPool) cudaEventDestroy(e);
+  for(auto e : ctx->marks) if(e) cudaEventDestroy(e);
   freeScene(ctx);
   freeWavefront(ctx);
   cudaFree(ctx->dEnv); cudaFree(ctx->dEnvAccel);
@@ -739,7 +741,8 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
           ScopedTimer t(ctx, timing, T_SHADOW);
           launchTraceShadow(ctx->stream, ctx->view, S, counting, ctx->numSMs);
         }
-        launchSwapQueues(ctx->stream, wf, dstats);
+        launchSwapQueues(ctx->stream, wf, dstats);  // device side: counts; host side: the two id arrays
+        std::swap(wf.queueCur, wf.queueNext);
         ctx->stats.kernel_launches += 4;
       }
       {
@@ -810,6 +813,24 @@ int vkrt_triangle_ids(vkrt_ctx* ctx, const uint32_t* tri_ids, uint32_t n, uint32
   return VKRT_OK;
 }
 
+int vkrt_mark(vkrt_ctx* ctx, int32_t which)
+{
+  if(!ctx || which < 0 || which > 1) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if(!ctx->marks[which]) CTX_CHECK(cudaEventCreate(&ctx->marks[which]));
+  CTX_CHECK(cudaEventRecord(ctx->marks[which], ctx->stream));
+  return VKRT_OK;
+}
+
+int vkrt_elapsed_ms(vkrt_ctx* ctx, float* out_ms)
+{
+  if(!ctx || !out_ms || !ctx->marks[0] || !ctx->marks[1]) return VKRT_ERR_STATE;
+  cudaSetDevice(ctx->device);
+  CTX_CHECK(cudaEventSynchronize(ctx->marks[1]));
+  CTX_CHECK(cudaEventElapsedTime(out_ms, ctx->marks[0], ctx->marks[1]));
+  return VKRT_OK;
+}
+
 int vkrt_get_stats(vkrt_ctx* ctx, vkrt_stats* out)
 {
   if(!ctx || !out) return VKRT_ERR_INVALID;
@@ -822,6 +843,9 @@ int vkrt_get_stats(vkrt_ctx* ctx, vkrt_stats* out)
   ctx->stats.shadow_rays   = ts.shadowRays;
   ctx->stats.nodes_visited = ts.nodesVisited;
   ctx->stats.tris_tested   = ts.trisTested;
+  ctx->stats.shadow_nodes_visited = ts.shadowNodes;
+  ctx->stats.shadow_tris_tested   = ts.shadowTris;
+  ctx->stats.bvh_max_depth        = (uint32_t)ctx->bvh.maxDepth;
   *out = ctx->stats;
   return VKRT_OK;
 }
@@ -837,6 +861,7 @@ int vkrt_reset_stats(vkrt_ctx* ctx)
   ctx->stats      = vkrt_stats{};
   ctx->stats.ms_build = keep.ms_build; ctx->stats.num_triangles = keep.num_triangles; ctx->stats.num_bvh_nodes = keep.num_bvh_nodes;
   ctx->stats.num_instances = keep.num_instances; ctx->stats.has_non_opaque = keep.has_non_opaque;
+  ctx->stats.bvh_max_depth = keep.bvh_max_depth;
   return VKRT_OK;
 }
 

@@ -83,7 +83,7 @@ struct Wavefront
 
 struct TraceStats  // device counters
 {
-  unsigned long long closestRays, shadowRays, nodesVisited, trisTested;
+  unsigned long long closestRays, shadowRays, nodesVisited, trisTested, shadowNodes, shadowTris;
 };
 
 }  // namespace vkrt

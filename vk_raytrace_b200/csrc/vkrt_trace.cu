@@ -247,6 +247,8 @@ __global__ void __launch_bounds__(kTraceBlock) traceShadowKernel(const __grid_co
   {
     atomicAdd(&L.stats->nodesVisited, (unsigned long long)nNodes);
     atomicAdd(&L.stats->trisTested, (unsigned long long)nTris);
+    atomicAdd(&L.stats->shadowNodes, (unsigned long long)nNodes);
+    atomicAdd(&L.stats->shadowTris, (unsigned long long)nTris);
   }
 }
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "vkrt_build_env_accel", "vkrt_set_environment", "vkrt_set_sunsky", "vkrt_set_camera", "vkrt_output_create",
     "vkrt_output_device_ptr", "vkrt_output_clear", "vkrt_output_read", "vkrt_tonemap", "vkrt_tonemap_float", "vkrt_render",
     "vkrt_sync", "vkrt_pack_vertices", "vkrt_make_camera", "vkrt_light_from_matrix", "vkrt_trace_rays", "vkrt_triangle_ids",
-    "vkrt_get_stats", "vkrt_reset_stats",
+    "vkrt_get_stats", "vkrt_reset_stats", "vkrt_mark", "vkrt_elapsed_ms",
 ]
 
 
@@ -69,5 +69,7 @@ def load_library():
     lib.vkrt_triangle_ids.argtypes = [vp, vp, u32, vp]
     lib.vkrt_get_stats.argtypes = [vp, C.POINTER(S.Stats)]
     lib.vkrt_reset_stats.argtypes = [vp]
+    lib.vkrt_mark.argtypes = [vp, i32]
+    lib.vkrt_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
     _LIB = lib
     return lib

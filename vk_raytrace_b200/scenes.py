@@ -353,7 +353,7 @@ def sponza_standin(detail=1.0, tex_size=512, env_size=(1024, 512), seed=99):
     in ~100 primMeshes over 25 materials; detail scales the tessellation (tests use ~0.05)."""
     rng = np.random.default_rng(seed)
     T = tex_size
-    d = max(detail, 0.01)
+    d = max(detail, 0.01) * 0.3265   # detail = 1.0 -> ~262k triangles (Sponza's count)
 
     def res(n, lo=2):
         return max(lo, int(round(n * math.sqrt(d))))
