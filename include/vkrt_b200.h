@@ -42,6 +42,7 @@ typedef struct vkrt_ctx vkrt_ctx;
  * src/accelstruct.cpp:110-162). */
 #define VKRT_BUILD_LBVH 0       /* GPU Morton/Karras LBVH (default) */
 #define VKRT_BUILD_LBVH_COLLAPSED 1 /* LBVH + bottom-up SAH leaf collapse */
+#define VKRT_BUILD_SAH_HOST 2       /* GPU flatten + host binned-SAH BVH2 (slow build, fast trace) */
 
 typedef struct vkrt_render_opts
 {

@@ -269,14 +269,16 @@ inline void considerTri(const Scene& s, uint32_t id, vec3 o, vec3 d, float tmax,
   best.t = t; best.u = u; best.v = v; best.tri = id;
 }
 
-inline bool slab(const BvhNode& n, vec3 o, vec3 inv, float tbest)
+// Conservative slab test; returns the entry distance through tnOut.
+inline bool slab(const BvhNode& n, vec3 o, vec3 inv, float tbest, float& tnOut)
 {
   float t0x = (n.lo[0] - o.x) * inv.x, t1x = (n.hi[0] - o.x) * inv.x;
   float t0y = (n.lo[1] - o.y) * inv.y, t1y = (n.hi[1] - o.y) * inv.y;
   float t0z = (n.lo[2] - o.z) * inv.z, t1z = (n.hi[2] - o.z) * inv.z;
   float tn  = std::fmax(std::fmax(std::fmin(t0x, t1x), std::fmin(t0y, t1y)), std::fmax(std::fmin(t0z, t1z), 0.0f));
   float tf  = std::fmin(std::fmin(std::fmax(t0x, t1x), std::fmax(t0y, t1y)), std::fmin(std::fmax(t0z, t1z), tbest));
-  return tn <= tf * 1.0002f;  // conservative: never reject a box MT could hit
+  tnOut     = tn;
+  return tn <= tf * 1.0002f;  // never reject a box the triangle test could hit
 }
 
 // closest != 0: nearest hit.  closest == 0: any hit (terminate on first accepted).
@@ -298,14 +300,16 @@ inline Hit traceRay(const Scene& s, vec3 o, vec3 d, float tmax, uint32_t raySeed
   auto     safeInv = [](float x) { return 1.0f / (std::fabs(x) < 1e-20f ? std::copysign(1e-20f, x) : x); };
   vec3     inv     = V3(safeInv(d.x), safeInv(d.y), safeInv(d.z));
   uint32_t stack[128];
-  int      sp    = 0;
-  stack[sp++]    = 0;
+  int      sp = 0;
+  float    tn;
+  if(cnt) cnt->nodes++;
+  if(!slab(s.bvh[0], o, inv, best.t, tn))
+    return best;
+  stack[sp++] = 0;
+  // The visiting order (near child first) only affects speed: acceptance is order independent.
   while(sp)
   {
     const BvhNode& n = s.bvh[stack[--sp]];
-    if(cnt) cnt->nodes++;
-    if(!slab(n, o, inv, best.t))
-      continue;
     if(n.right & 0x80000000u)
     {
       uint32_t cntTri = n.right & 0x7fffffffu;
@@ -316,12 +320,29 @@ inline Hit traceRay(const Scene& s, vec3 o, vec3 d, float tmax, uint32_t raySeed
       }
       if(!closest && best.tri != ~0u)
         return best;
+      continue;
     }
-    else
+    float tl, tr;
+    bool  hl = slab(s.bvh[n.left], o, inv, best.t, tl);
+    bool  hr = slab(s.bvh[n.right], o, inv, best.t, tr);
+    if(cnt) cnt->nodes += 2;
+    if(hl && hr)
     {
-      stack[sp++] = n.left;
-      stack[sp++] = n.right;
+      if(tr < tl)
+      {
+        stack[sp++] = n.left;
+        stack[sp++] = n.right;
+      }
+      else
+      {
+        stack[sp++] = n.right;
+        stack[sp++] = n.left;
+      }
     }
+    else if(hl)
+      stack[sp++] = n.left;
+    else if(hr)
+      stack[sp++] = n.right;
   }
   return best;
 }

@@ -341,16 +341,19 @@ int oracle_render(OracleCtx* c, const RtxState* state, int32_t num_frames, int32
   {
     RtxState st = *state;
     st.frame    = state->frame + f;
-    std::atomic<int> next{row_begin};
+    // work item = a 128-pixel segment of a row (keeps 100+ threads balanced)
+    const int        segs = (W + 127) / 128;
+    std::atomic<int> next{row_begin * segs};
     std::mutex       mtx;
     auto work = [&]() {
       RenderCounters local;
       for(;;)
       {
-        int y = next.fetch_add(1);
-        if(y >= row_end)
+        int item = next.fetch_add(1);
+        if(item >= row_end * segs)
           break;
-        for(int x = 0; x < W; x++)
+        const int y = item / segs, x0 = (item % segs) * 128;
+        for(int x = x0; x < std::min(W, x0 + 128); x++)
           renderPixel(c->scene, st, seed_mode, x, y, c->image.data(), &local);
       }
       std::lock_guard<std::mutex> g(mtx);

@@ -133,9 +133,10 @@ def test_sponza_with_alpha_textures_lights(vk, ob, gpu, pbr, seed_mode):
     a, b = gpu.output_read()[..., :3], o.output_read()[..., :3]
     assert np.isfinite(a).all()
     # a few pixels may take a different branch because of ulp differences in sin/cos/pow: bounded count, bounded L2
-    off = (np.abs(a - b) > 1e-3 * (1 + np.abs(b))).any(axis=2).sum()
-    assert off <= 0.005 * W * H, off
-    assert per_channel_rel_l2(a, b) < 1e-3
+    # (at this tiny size one divergent path is already 1e-2 of the image norm, so the L2 bound is taken over the rest)
+    off = (np.abs(a - b) > 1e-3 * (1 + np.abs(b))).any(axis=2)
+    assert off.sum() <= 0.005 * W * H, off.sum()
+    assert per_channel_rel_l2(a[~off], b[~off]) < IMG_TOL
 
 
 def test_multi_sample_frames_and_clamp(vk, ob, gpu):
@@ -267,5 +268,5 @@ def test_full_size_properties_sponza_1080p(vk, gpu, build_mode):
     o.render(st, 3, rows=rows)
     ref = o.output_read()[rows[0]:rows[1], :, :3]
     got = a[rows[0]:rows[1], :, :3]
-    off = (np.abs(got - ref) > 1e-3 * (1 + np.abs(ref))).any(axis=2).mean()
-    assert off < 0.005 and per_channel_rel_l2(got, ref) < 1e-3
+    off = (np.abs(got - ref) > 1e-3 * (1 + np.abs(ref))).any(axis=2)
+    assert off.mean() < 0.002 and per_channel_rel_l2(got[~off], ref[~off]) < IMG_TOL

@@ -456,6 +456,26 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
     return VKRT_ERR_CUDA;
   }
   ctx->stats.kernel_launches += launches;
+  if(build_mode == VKRT_BUILD_SAH_HOST && totalTris > 0)
+  {
+    // re-organise the GPU-flattened triangles under a host-built binned-SAH tree
+    const uint32_t nt = (uint32_t)totalTris;
+    std::vector<float>    htris(12ull * nt), hnodes, sorted(12ull * nt);
+    std::vector<uint32_t> order;
+    int                   depth = 0;
+    CTX_CHECK(cudaMemcpy(htris.data(), ctx->bvh.tris, sizeof(float) * 12ull * nt, cudaMemcpyDeviceToHost));
+    if(!buildSahHost(htris.data(), nt, hnodes, order, depth))
+      return fail(ctx, VKRT_ERR_INVALID, "scene_commit: host SAH build failed");
+    for(uint32_t i = 0; i < nt; i++)
+      std::memcpy(&sorted[12ull * i], &htris[12ull * order[i]], 48);
+    cudaFree(ctx->bvh.nodes);
+    ctx->bvh.nodes = nullptr;
+    ctx->bvh.numNodes = (uint32_t)(hnodes.size() / 16);
+    CTX_CHECK(cudaMalloc(&ctx->bvh.nodes, hnodes.size() * sizeof(float)));
+    CTX_CHECK(cudaMemcpy(ctx->bvh.nodes, hnodes.data(), hnodes.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CTX_CHECK(cudaMemcpy(ctx->bvh.tris, sorted.data(), sorted.size() * sizeof(float), cudaMemcpyHostToDevice));
+    ctx->bvh.maxDepth = depth;
+  }
   cudaEventRecord(e1, ctx->stream);
   CTX_CHECK(cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
@@ -780,15 +800,34 @@ int vkrt_trace_rays(vkrt_ctx* ctx, const float* rays, uint32_t n, int32_t closes
   if(!ctx->committed) return fail(ctx, VKRT_ERR_STATE, "trace_rays: scene not committed");
   if(n == 0) return VKRT_OK;
   cudaSetDevice(ctx->device);
-  float4 *dR = nullptr, *dH = nullptr;
-  CTX_CHECK(cudaMalloc(&dR, (size_t)n * 32));
+  // de-interleave {o,tmax,d,seed} into the two float4 streams the trace kernels read
+  std::vector<float4> ho(n), hd(n);
+  for(uint32_t i = 0; i < n; i++)
+  {
+    const float* r = rays + (size_t)i * 8;
+    ho[i] = make_float4(r[0], r[1], r[2], r[3]);
+    hd[i] = make_float4(r[4], r[5], r[6], r[7]);
+  }
+  float4 *dO = nullptr, *dD = nullptr, *dH = nullptr;
+  uint32_t* dCnt = nullptr;
+  CTX_CHECK(cudaMalloc(&dO, (size_t)n * 16));
+  CTX_CHECK(cudaMalloc(&dD, (size_t)n * 16));
   CTX_CHECK(cudaMalloc(&dH, (size_t)n * 16));
-  cudaMemcpyAsync(dR, rays, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream);
-  launchTraceProbe(ctx->stream, ctx->view, dR, n, closest != 0, dH);
+  CTX_CHECK(cudaMalloc(&dCnt, 8));
+  const uint32_t cc[2] = {n, 0u};
+  cudaMemcpyAsync(dO, ho.data(), (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(dD, hd.data(), (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(dCnt, cc, 8, cudaMemcpyHostToDevice, ctx->stream);
+  TraceLaunch L{};
+  L.rayO = dO; L.rayD = dD; L.queue = nullptr; L.count = dCnt; L.cursor = dCnt + 1; L.hit = dH;
+  if(closest)
+    launchTraceClosest(ctx->stream, ctx->view, L, false, ctx->numSMs);
+  else
+    launchTraceAnyProbe(ctx->stream, ctx->view, L, ctx->numSMs);
   ctx->stats.kernel_launches++;
   cudaMemcpyAsync(out_hits, dH, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(dR); cudaFree(dH);
+  cudaFree(dO); cudaFree(dD); cudaFree(dH); cudaFree(dCnt);
   if(e != cudaSuccess)
   {
     ctx->err = std::string("trace_rays: ") + cudaGetErrorString(e);

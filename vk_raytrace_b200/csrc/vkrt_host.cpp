@@ -219,3 +219,181 @@ int vkrt_light_from_matrix(const float m[16], Light* l)
 }
 
 }  // extern "C"
+
+// ---- host binned-SAH builder (VKRT_BUILD_SAH_HOST) ----------------------------------------------------
+// The "prefer fast trace" analogue of the driver build the reference requests
+// (VK_BUILD_ACCELERATION_STRUCTURE_PREFER_FAST_TRACE_BIT_KHR, src/accelstruct.cpp:125-126): a top-down
+// binned surface-area-heuristic BVH2 over the world-space triangles the GPU flatten pass produced, emitted
+// in the same 64-byte node format as the GPU LBVH.  Slower to build, fewer nodes per ray.
+#include <atomic>
+#include <future>
+namespace vkrt {
+namespace {
+struct SahBuild
+{
+  const float*          tris;  // n x 12 floats (3 x float4)
+  std::vector<float>    lo, hi, ce;  // n x 3
+  std::vector<uint32_t> order;
+  float*                nodes;  // 16 floats per node
+  std::atomic<uint32_t> nextNode{1};
+  std::atomic<int>      maxDepth{0};
+};
+struct Bounds
+{
+  float lo[3], hi[3];
+  void  reset() { for(int k = 0; k < 3; k++) { lo[k] = 3e38f; hi[k] = -3e38f; } }
+  void  grow(const float* l, const float* h) { for(int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], l[k]); hi[k] = std::max(hi[k], h[k]); } }
+  float area() const { float x = hi[0] - lo[0], y = hi[1] - lo[1], z = hi[2] - lo[2]; return 2.f * (x * y + y * z + z * x); }
+};
+constexpr int   kBins = 32;
+constexpr uint32_t kLeafMax = 4;
+
+uint32_t sahRecurse(SahBuild& B, uint32_t b, uint32_t e, Bounds& outBox, int depth, int par)
+{
+  const uint32_t n = e - b;
+  Bounds box, cbox;
+  box.reset(); cbox.reset();
+  for(uint32_t i = b; i < e; i++)
+  {
+    const uint32_t t = B.order[i];
+    box.grow(&B.lo[3 * t], &B.hi[3 * t]);
+    cbox.grow(&B.ce[3 * t], &B.ce[3 * t]);
+  }
+  outBox = box;
+  auto makeLeaf = [&]() -> uint32_t {
+    int d = B.maxDepth.load();
+    while(depth > d && !B.maxDepth.compare_exchange_weak(d, depth)) {}
+    return 0x80000000u | ((n - 1) << 28) | b;
+  };
+  if(n == 1)
+    return makeLeaf();
+  // binned SAH over the widest centroid axes
+  int   bestAxis = -1, bestBin = -1;
+  float bestCost = 3e38f;
+  for(int a = 0; a < 3; a++)
+  {
+    const float cmin = cbox.lo[a], cmax = cbox.hi[a];
+    if(!(cmax > cmin))
+      continue;
+    Bounds   bb[kBins];
+    uint32_t bc[kBins] = {0};
+    for(int k = 0; k < kBins; k++) bb[k].reset();
+    const float scale = (float)kBins / (cmax - cmin);
+    for(uint32_t i = b; i < e; i++)
+    {
+      const uint32_t t = B.order[i];
+      int k = std::min(kBins - 1, (int)((B.ce[3 * t + a] - cmin) * scale));
+      bc[k]++;
+      bb[k].grow(&B.lo[3 * t], &B.hi[3 * t]);
+    }
+    float    rA[kBins];
+    uint32_t rC[kBins];
+    Bounds   acc;
+    acc.reset();
+    uint32_t c = 0;
+    for(int k = kBins - 1; k > 0; k--)
+    {
+      if(bc[k]) acc.grow(bb[k].lo, bb[k].hi);
+      c += bc[k];
+      rA[k] = c ? acc.area() : 0.f;
+      rC[k] = c;
+    }
+    acc.reset();
+    c = 0;
+    for(int k = 0; k < kBins - 1; k++)
+    {
+      if(bc[k]) acc.grow(bb[k].lo, bb[k].hi);
+      c += bc[k];
+      if(c == 0 || rC[k + 1] == 0)
+        continue;
+      const float cost = acc.area() * (float)c + rA[k + 1] * (float)rC[k + 1];
+      if(cost < bestCost) { bestCost = cost; bestAxis = a; bestBin = k; }
+    }
+  }
+  const float leafCost = box.area() * (float)n;
+  if(n <= kLeafMax && (bestAxis < 0 || leafCost <= 1.0f * box.area() + bestCost))
+    return makeLeaf();
+  uint32_t mid;
+  if(bestAxis >= 0)
+  {
+    const float cmin = cbox.lo[bestAxis], scale = (float)kBins / (cbox.hi[bestAxis] - cmin);
+    auto it = std::partition(B.order.begin() + b, B.order.begin() + e, [&](uint32_t t) {
+      return std::min(kBins - 1, (int)((B.ce[3 * t + bestAxis] - cmin) * scale)) <= bestBin;
+    });
+    mid = (uint32_t)(it - B.order.begin());
+    if(mid == b || mid == e)
+      mid = b + n / 2;
+  }
+  else
+  {
+    if(n <= 8)
+      return makeLeaf();  // coincident centroids: up to 8 triangles fit a leaf
+    mid = b + n / 2;
+  }
+  const uint32_t idx = B.nextNode.fetch_add(1);
+  Bounds         lb, rb;
+  uint32_t       lc, rc;
+  if(par > 0 && n > 20000)
+  {
+    auto fut = std::async(std::launch::async, [&]() { return sahRecurse(B, b, mid, lb, depth + 1, par - 1); });
+    rc       = sahRecurse(B, mid, e, rb, depth + 1, par - 1);
+    lc       = fut.get();
+  }
+  else
+  {
+    lc = sahRecurse(B, b, mid, lb, depth + 1, 0);
+    rc = sahRecurse(B, mid, e, rb, depth + 1, 0);
+  }
+  float* N = B.nodes + 16ull * idx;
+  N[0] = lb.lo[0]; N[1] = lb.hi[0]; N[2] = lb.lo[1]; N[3] = lb.hi[1];
+  N[4] = rb.lo[0]; N[5] = rb.hi[0]; N[6] = rb.lo[1]; N[7] = rb.hi[1];
+  N[8] = lb.lo[2]; N[9] = lb.hi[2]; N[10] = rb.lo[2]; N[11] = rb.hi[2];
+  std::memcpy(&N[12], &lc, 4);
+  std::memcpy(&N[13], &rc, 4);
+  N[14] = 0.f; N[15] = 0.f;
+  return idx;
+}
+}  // namespace
+
+// tris: n x 12 floats in any order.  Outputs nodes (16 floats each) and the permutation to apply to `tris`.
+bool buildSahHost(const float* tris, uint32_t n, std::vector<float>& nodesOut, std::vector<uint32_t>& orderOut, int& maxDepthOut)
+{
+  if(n == 0)
+    return false;
+  SahBuild B;
+  B.tris = tris;
+  B.lo.resize(3ull * n); B.hi.resize(3ull * n); B.ce.resize(3ull * n);
+  B.order.resize(n);
+  for(uint32_t i = 0; i < n; i++)
+  {
+    const float* t = tris + 12ull * i;
+    for(int k = 0; k < 3; k++)
+    {
+      const float l = std::min(t[k], std::min(t[4 + k], t[8 + k])), h = std::max(t[k], std::max(t[4 + k], t[8 + k]));
+      B.lo[3ull * i + k] = l; B.hi[3ull * i + k] = h; B.ce[3ull * i + k] = (l + h) * 0.5f;
+    }
+    B.order[i] = i;
+  }
+  nodesOut.assign(16ull * std::max<uint32_t>(n, 2), 0.f);
+  B.nodes = nodesOut.data();
+  // node 0 is the root and must be an inner node: build the two halves of the top split into it
+  Bounds   rootBox;
+  B.nextNode = 0;
+  uint32_t root = sahRecurse(B, 0, n, rootBox, 0, 3);
+  if(root & 0x80000000u)
+  {
+    // the whole scene fits one leaf: make a root whose two children are that leaf
+    float* N = B.nodes;
+    N[0] = rootBox.lo[0]; N[1] = rootBox.hi[0]; N[2] = rootBox.lo[1]; N[3] = rootBox.hi[1];
+    N[4] = N[0]; N[5] = N[1]; N[6] = N[2]; N[7] = N[3];
+    N[8] = rootBox.lo[2]; N[9] = rootBox.hi[2]; N[10] = N[8]; N[11] = N[9];
+    std::memcpy(&N[12], &root, 4);
+    std::memcpy(&N[13], &root, 4);
+    B.nextNode = 1;
+  }
+  nodesOut.resize(16ull * B.nextNode.load());
+  orderOut    = std::move(B.order);
+  maxDepthOut = B.maxDepth.load();
+  return true;
+}
+}  // namespace vkrt

@@ -1,6 +1,7 @@
 // vkrt_internal.h -- host-side declarations shared by the translation units of libvkrt_b200.
 #pragma once
 #include <string>
+#include <vector>
 #include <cuda_runtime.h>
 #include "../../include/vkrt_b200.h"
 
@@ -41,7 +42,7 @@ struct TraceLaunch
 };
 void launchTraceClosest(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, bool count, int numSMs);
 void launchTraceShadow(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, bool count, int numSMs);
-void launchTraceProbe(cudaStream_t s, const SceneView& scene, const float4* rays, uint32_t n, bool closest, float4* out);
+void launchTraceAnyProbe(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, int numSMs);
 
 // vkrt_shade.cu
 struct FrameParams
@@ -62,5 +63,6 @@ void launchTonemap(cudaStream_t s, const float4* image, int w, int h, const Tone
 // vkrt_host.cpp
 void buildEnvAccelHost(const float* rgba, uint32_t w, uint32_t h, EnvAccel* out, float* integral, float* average);
 bool invertAffine(const float* m16, float* inv16);
+bool buildSahHost(const float* tris, uint32_t n, std::vector<float>& nodesOut, std::vector<uint32_t>& orderOut, int& maxDepthOut);
 
 }  // namespace vkrt
