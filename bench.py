@@ -136,7 +136,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sponza_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--pbr-mode", type=int, default=0)
-    ap.add_argument("--build-mode", type=int, default=0)
+    ap.add_argument("--build-mode", type=int, default=1, help="0 LBVH, 1 LBVH + SAH leaf collapse (default), 2 host binned SAH")
     ap.add_argument("--frames-in-flight", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

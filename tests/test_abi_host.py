@@ -118,6 +118,20 @@ def test_make_camera(vk):
     assert abs(cam.focalDist - np.linalg.norm(want)) < 1e-5 and cam.nbLights == 3 and abs(cam.aperture - 0.1) < 1e-7
     # projInverse maps NDC (0,0,1) onto the -Z axis and y is flipped (proj[1][1] *= -1)
     t = pi @ np.array([0, 0, 1, 1.0])
-    assert abs(t[0]) < 1e-6 and abs(t[1]) < 1e-6 and t[2] / t[3] < 0
+    assert abs(t[0]) < 1e-6 and abs(t[1]) < 1e-6 and t[2] < 0
     up = pi @ np.array([0, -1, 1, 1.0])
     assert up[1] / abs(up[2]) > 0 and abs(up[1] / -up[2] - np.tan(np.radians(45.0) / 2)) < 1e-5
+
+
+def test_cpp_renderer_adaptor_compiles_and_fails_loudly_without_gpu(vk):
+    """The C++ `CudaRenderer : Renderer` adaptor builds against the C ABI; without a GPU it reports the error."""
+    import subprocess, torch
+    import __graft_entry__ as g
+    host = os.path.join(ROOT, "vk_raytrace_b200", "host")
+    exe = os.path.join(host, "vkrt_headless")
+    if not os.path.exists(exe):
+        g.build()
+    assert os.path.exists(exe)
+    if not torch.cuda.is_available():
+        out = subprocess.run([exe, "1"], capture_output=True, text=True, cwd=host)
+        assert out.returncode == 2 and "vkrt_create" in out.stderr

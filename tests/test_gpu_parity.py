@@ -270,3 +270,16 @@ def test_full_size_properties_sponza_1080p(vk, gpu, build_mode):
     got = a[rows[0]:rows[1], :, :3]
     off = (np.abs(got - ref) > 1e-3 * (1 + np.abs(ref))).any(axis=2)
     assert off.mean() < 0.002 and per_channel_rel_l2(got[~off], ref[~off]) < IMG_TOL
+
+
+def test_cpp_renderer_adaptor_headless(vk):
+    """`CudaRenderer : Renderer` (vk_raytrace_b200/host/) driven like src/main.cpp drives a back-end."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "vk_raytrace_b200", "host", "vkrt_headless")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    out = subprocess.run([exe, "8"], capture_output=True, text=True, cwd=os.path.dirname(exe), timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "8 frames" in out.stdout and float(out.stdout.split("mean green")[1].split()[0]) > 20.0

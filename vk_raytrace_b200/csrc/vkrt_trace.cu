@@ -319,6 +319,331 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernel(const __grid_const
   }
 }
 
+
+// ==========================================================================================================
+// Warp-cooperative variant ("leaf queue").  Lanes own rays for the box tests, but triangle tests are handed to
+// a warp-shared queue in shared memory and executed 32 at a time by whichever lanes are free, so neither phase
+// runs with a handful of active lanes:
+//   node phase   every lane whose ray still has inner nodes does one node step; leaf children are appended to
+//                the queue as (owner lane, leaf code); the lane keeps descending with its current best t
+//                (speculative: best t only shrinks, so stale values just cost extra visits);
+//   leaf phase   when >= 32 items wait (or the node phase runs dry) each lane takes one item, reads the owner's
+//                ray through warp shuffles and resolves the result with a 64-bit shared-memory atomicMin on
+//                (t bits << 32 | triangle id) -- exactly the "nearest t, ties to the lower id" rule.
+// A ray is finished when its stack is empty and none of its items are pending; finished lanes are refilled from
+// the global cursor.  Results are identical to the per-lane kernel (acceptance is order independent).
+// ==========================================================================================================
+constexpr int kQCap     = 128;  // leaf-queue capacity per warp
+constexpr int kNodeIter = 12;   // node steps between refill checks
+
+struct WarpShared
+{
+  unsigned long long bestKey[32];
+  float2             bestUV[32];
+  int                pend[32];
+  uint2              queue[kQCap];
+};
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, 8) traceKernelCoop(const __grid_constant__ SceneView sc, const __grid_constant__ TraceLaunch L)
+{
+  __shared__ uint32_t   s_stack[kStackShared * kTraceBlock];
+  __shared__ WarpShared s_ws[kTraceBlock / 32];
+  uint32_t* const sstack = &s_stack[threadIdx.x];
+  WarpShared&     ws     = s_ws[threadIdx.x >> 5];
+  uint32_t        lstack[kStackLocal];
+  const uint32_t  n    = *L.count;
+  const uint32_t  lane = threadIdx.x & 31u;
+  const unsigned  lt   = (1u << lane) - 1u;
+
+  if(sc.numTris == 0)
+  {
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+      const uint32_t slot = (MODE != MODE_SHADOW_RESOLVE && L.queue) ? L.queue[i] : i;
+      if(MODE == MODE_SHADOW_RESOLVE)
+      {
+        const float4 c = L.shC[i];
+        float4       r = L.rad[__float_as_uint(c.w)];
+        r.x += c.x; r.y += c.y; r.z += c.z;
+        L.rad[__float_as_uint(c.w)] = r;
+      }
+      else
+        L.hit[slot] = f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u));
+    }
+    return;
+  }
+
+  const float4* __restrict__ nodes = sc.nodes;
+  const float4* __restrict__ tris  = sc.tris;
+
+  bool     haveRay = false;
+  uint32_t slot = 0, seed = 0;
+  float3   o = f3(0.f), d = f3(0.f), id = f3(0.f);
+  float    tmax = 0.f;
+  uint32_t node = kDone;
+  int      sp = 0;
+  int      qcount = 0;          // warp uniform
+  bool     exhausted = false;   // warp uniform
+  uint32_t nNodes = 0, nTris = 0;
+  ws.pend[lane] = 0;
+
+  auto push = [&](uint32_t v) {
+    if(sp < kStackShared)
+      sstack[sp * kTraceBlock] = v;
+    else
+      lstack[min(sp - kStackShared, kStackLocal - 1)] = v;
+    sp++;
+  };
+  auto pop = [&]() -> uint32_t {
+    if(sp == 0)
+      return kDone;
+    --sp;
+    return sp < kStackShared ? sstack[sp * kTraceBlock] : lstack[min(sp - kStackShared, kStackLocal - 1)];
+  };
+
+  for(;;)
+  {
+    __syncwarp();
+    // ---- refill idle lanes -----------------------------------------------------------------------
+    const unsigned idle = __ballot_sync(kFull, !haveRay);
+    if(idle && !exhausted)
+    {
+      const uint32_t want = (uint32_t)__popc(idle);
+      uint32_t       base = 0;
+      if(lane == 0)
+        base = atomicAdd(L.cursor, want);
+      base = __shfl_sync(kFull, base, 0);
+      if(!haveRay)
+      {
+        const uint32_t i = base + (uint32_t)__popc(idle & lt);
+        if(i < n)
+        {
+          slot = (MODE != MODE_SHADOW_RESOLVE && L.queue) ? L.queue[i] : i;
+          const float4 ro = L.rayO[slot], rd = L.rayD[slot];
+          o = f3(ro); d = f3(rd);
+          tmax = ro.w; seed = __float_as_uint(rd.w);
+          id   = f3(safeInv(d.x), safeInv(d.y), safeInv(d.z));
+          ws.bestKey[lane] = ((unsigned long long)__float_as_uint(tmax) << 32) | 0xffffffffull;
+          ws.pend[lane]    = 0;
+          node = 0; sp = 0;
+          haveRay = true;
+        }
+      }
+      exhausted = (base + want >= n);
+    }
+    if(!__any_sync(kFull, haveRay))
+      break;
+    __syncwarp();
+
+    // ---- node phase ---------------------------------------------------------------------------------
+    for(int it = 0; it < kNodeIter; it++)
+    {
+      const unsigned long long myKey = ws.bestKey[lane];
+      const bool found = (MODE != MODE_CLOSEST) && haveRay && (uint32_t)myKey != 0xffffffffu;  // any-hit: stop descending
+      const bool work  = haveRay && node != kDone && !found;
+      const unsigned wmask = __ballot_sync(kFull, work);
+      if(wmask == 0 || qcount > kQCap - 64)
+        break;
+      bool     l0 = false, l1 = false;
+      uint32_t c0 = 0, c1 = 0;
+      if(work)
+      {
+        const float  bestT = __uint_as_float((uint32_t)(myKey >> 32));
+        const float4 n0 = __ldg(&nodes[4ull * node + 0]);
+        const float4 n1 = __ldg(&nodes[4ull * node + 1]);
+        const float4 n2 = __ldg(&nodes[4ull * node + 2]);
+        const float4 n3 = __ldg(&nodes[4ull * node + 3]);
+        if(COUNT) nNodes++;
+        const float a0x = (n0.x - o.x) * id.x, b0x = (n0.y - o.x) * id.x;
+        const float a0y = (n0.z - o.y) * id.y, b0y = (n0.w - o.y) * id.y;
+        const float a0z = (n2.x - o.z) * id.z, b0z = (n2.y - o.z) * id.z;
+        const float a1x = (n1.x - o.x) * id.x, b1x = (n1.y - o.x) * id.x;
+        const float a1y = (n1.z - o.y) * id.y, b1y = (n1.w - o.y) * id.y;
+        const float a1z = (n2.z - o.z) * id.z, b1z = (n2.w - o.z) * id.z;
+        const float tn0 = fmaxf(fmaxf(fminf(a0x, b0x), fminf(a0y, b0y)), fmaxf(fminf(a0z, b0z), 0.0f));
+        const float tf0 = fminf(fminf(fmaxf(a0x, b0x), fmaxf(a0y, b0y)), fminf(fmaxf(a0z, b0z), bestT));
+        const float tn1 = fmaxf(fmaxf(fminf(a1x, b1x), fminf(a1y, b1y)), fmaxf(fminf(a1z, b1z), 0.0f));
+        const float tf1 = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fminf(fmaxf(a1z, b1z), bestT));
+        const bool  h0  = tn0 <= tf0 * 1.0002f;  // conservative: never reject a box the triangle test could hit
+        const bool  h1  = tn1 <= tf1 * 1.0002f;
+        c0 = __float_as_uint(n3.x);
+        c1 = __float_as_uint(n3.y);
+        l0 = h0 && (c0 & kLeafBit);
+        l1 = h1 && (c1 & kLeafBit);
+        const bool i0 = h0 && !(c0 & kLeafBit);
+        const bool i1 = h1 && !(c1 & kLeafBit);
+        if(i0 && i1)
+        {
+          if(tn1 < tn0)
+          {
+            push(c0);
+            node = c1;
+          }
+          else
+          {
+            push(c1);
+            node = c0;
+          }
+        }
+        else if(i0)
+          node = c0;
+        else if(i1)
+          node = c1;
+        else
+          node = pop();
+      }
+      // append leaf children to the warp queue (uniform code)
+      const unsigned m0 = __ballot_sync(kFull, l0);
+      const unsigned m1 = __ballot_sync(kFull, l1);
+      if(l0)
+        ws.queue[qcount + __popc(m0 & lt)] = make_uint2(lane, c0);
+      if(l1)
+        ws.queue[qcount + __popc(m0) + __popc(m1 & lt)] = make_uint2(lane, c1);
+      if(l0 || l1)
+        ws.pend[lane] += (l0 ? 1 : 0) + (l1 ? 1 : 0);
+      qcount += __popc(m0) + __popc(m1);
+      if(qcount >= 32 && __popc(wmask) < 24)
+        break;  // enough triangle work for a full batch and the node phase is thinning out
+    }
+    __syncwarp();
+
+    // ---- leaf phase -----------------------------------------------------------------------------------
+    {
+      const unsigned stillWork = __ballot_sync(kFull, haveRay && node != kDone);
+      // drain in full batches; take the remainder too when the node phase has (almost) nothing left
+      while(qcount >= 32 || (qcount > 0 && (__popc(stillWork) < 16 || qcount > kQCap - 64)))
+      {
+        const int  batch = min(32, qcount);
+        const bool valid = (int)lane < batch;
+        uint2      item  = make_uint2(lane, 0u);
+        if(valid)
+          item = ws.queue[qcount - batch + lane];
+        const int   owner = (int)item.x;
+        const float rox = __shfl_sync(kFull, o.x, owner), roy = __shfl_sync(kFull, o.y, owner), roz = __shfl_sync(kFull, o.z, owner);
+        const float rdx = __shfl_sync(kFull, d.x, owner), rdy = __shfl_sync(kFull, d.y, owner), rdz = __shfl_sync(kFull, d.z, owner);
+        const float rtmax = __shfl_sync(kFull, tmax, owner);
+        const uint32_t rseed = __shfl_sync(kFull, seed, owner);
+        unsigned long long cand = ~0ull;
+        float cu = 0.f, cv = 0.f;
+        if(valid)
+        {
+          const float3 ro = f3(rox, roy, roz), rd = f3(rdx, rdy, rdz);
+          const uint32_t first = item.y & kLeafMask;
+          const uint32_t cnt   = ((item.y >> kLeafCntSh) & 7u) + 1u;
+          unsigned long long cur = ws.bestKey[owner];   // may be stale: only used to skip work
+          for(uint32_t k = 0; k < cnt; k++)
+          {
+            const float4 q0 = __ldg(&tris[3ull * (first + k) + 0]);
+            const float4 q1 = __ldg(&tris[3ull * (first + k) + 1]);
+            const float4 q2 = __ldg(&tris[3ull * (first + k) + 2]);
+            if(COUNT) nTris++;
+            const uint32_t flags = __float_as_uint(q0.w);
+            const uint32_t triId = __float_as_uint(q1.w);
+            // Moller-Trumbore, pinned operation order (no FMA: -fmad=false)
+            const float3 v0  = f3(q0);
+            const float3 e1  = f3(q1) - v0;
+            const float3 e2  = f3(q2) - v0;
+            const float3 p   = cross(rd, e2);
+            const float  det = dot(e1, p);
+            if(!(flags & TRI_CULL_DISABLE))
+            {
+              const bool front = (flags & TRI_FLIP_FACING) ? (det < 0.0f) : (det > 0.0f);
+              if(!front)
+                continue;
+            }
+            if(det == 0.0f || !(det == det))
+              continue;
+            const float  inv = 1.0f / det;
+            const float3 tv  = ro - v0;
+            const float  u   = dot(tv, p) * inv;
+            if(!(u >= 0.0f && u <= 1.0f))
+              continue;
+            const float3 q = cross(tv, e1);
+            const float  v = dot(rd, q) * inv;
+            if(!(v >= 0.0f && (u + v) <= 1.0f))
+              continue;
+            const float t = dot(e2, q) * inv;
+            if(!(t > 0.0f && t < rtmax))
+              continue;
+            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | triId;
+            if(!(key < cur && key < cand))
+              continue;
+            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, u, v, rseed))
+              continue;
+            cand = key; cu = u; cv = v;
+          }
+          if(cand != ~0ull)
+            atomicMin(&ws.bestKey[owner], cand);
+        }
+        __syncwarp();
+        if(valid)
+        {
+          if(cand != ~0ull && ws.bestKey[owner] == cand)
+            ws.bestUV[owner] = make_float2(cu, cv);
+          atomicSub(&ws.pend[owner], 1);
+        }
+        __syncwarp();
+        qcount -= batch;
+      }
+    }
+
+    // ---- finished rays -----------------------------------------------------------------------------------
+    if(haveRay)
+    {
+      const unsigned long long key = ws.bestKey[lane];
+      const bool hitFound = (uint32_t)key != 0xffffffffu;
+      const bool finished = ((node == kDone) || (MODE != MODE_CLOSEST && hitFound)) && ws.pend[lane] == 0;
+      if(finished)
+      {
+        if(MODE == MODE_CLOSEST)
+        {
+          const float2 uv = ws.bestUV[lane];
+          L.hit[slot] = hitFound ? f4(__uint_as_float((uint32_t)(key >> 32)), uv.x, uv.y, __uint_as_float((uint32_t)key))
+                                 : f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u));
+        }
+        else if(MODE == MODE_ANY_PROBE)
+          L.hit[slot] = hitFound ? f4(0.f, 0.f, 0.f, __uint_as_float(0u)) : f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u));
+        else if(!hitFound)
+        {
+          const float4   c    = L.shC[slot];
+          const uint32_t path = __float_as_uint(c.w);
+          float4         rad  = L.rad[path];
+          rad.x += c.x; rad.y += c.y; rad.z += c.z;
+          L.rad[path] = rad;
+        }
+        haveRay = false;
+        node    = kDone;
+        sp      = 0;
+      }
+    }
+  }
+
+  if(COUNT && L.stats)
+  {
+    atomicAdd(&L.stats->nodesVisited, (unsigned long long)nNodes);
+    atomicAdd(&L.stats->trisTested, (unsigned long long)nTris);
+    if(MODE == MODE_SHADOW_RESOLVE)
+    {
+      atomicAdd(&L.stats->shadowNodes, (unsigned long long)nNodes);
+      atomicAdd(&L.stats->shadowTris, (unsigned long long)nTris);
+    }
+  }
+}
+
+template <int MODE, bool COUNT>
+static void launchTraceCoop(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, int numSMs)
+{
+  static int grid = 0;
+  if(!grid)
+  {
+    int perSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernelCoop<MODE, COUNT>, kTraceBlock, 0);
+    grid = numSMs * (perSM < 1 ? 1 : perSM);
+  }
+  traceKernelCoop<MODE, COUNT><<<grid, kTraceBlock, 0, s>>>(scene, L);
+}
+
 template <int MODE, bool COUNT, int VARIANT>
 static void launchTraceV(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, int numSMs)
 {
@@ -338,10 +663,11 @@ static void launchTrace(cudaStream_t s, const SceneView& scene, const TraceLaunc
   if(variant < 0)
   {
     const char* e = getenv("VKRT_TRACE_VARIANT");
-    variant       = e ? atoi(e) : 0;
+    variant       = e ? atoi(e) : 8;  // default: leave the node loop when <= 8 lanes are still searching
   }
   switch(variant)
   {
+    case 100: launchTraceCoop<MODE, COUNT>(s, scene, L, numSMs); break;
     case 1: launchTraceV<MODE, COUNT, 1>(s, scene, L, numSMs); break;
     case 4: launchTraceV<MODE, COUNT, 4>(s, scene, L, numSMs); break;
     case 8: launchTraceV<MODE, COUNT, 8>(s, scene, L, numSMs); break;
