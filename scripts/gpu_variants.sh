@@ -1,6 +1,6 @@
 #!/bin/bash
 # quick A/B of traversal-kernel variants and BVH build modes (bring-up helper)
-for bm in 0 2; do for v in 8 100; do
+for bm in 1; do for v in 8 200; do
   VKRT_TRACE_VARIANT=$v python bench.py --steps 16 --warmup 3 --no-cpu-baseline --no-e2e --build-mode $bm 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=d['kernel_ms']; r=d['roofline']

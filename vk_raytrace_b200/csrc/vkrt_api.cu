@@ -117,7 +117,7 @@ static void freeScene(vkrt_ctx* c)
   cudaFree(c->dMat); cudaFree(c->dLights); cudaFree(c->dTexDescs);
   for(auto p : c->dTexData) cudaFree(p);
   c->dTexData.clear();
-  cudaFree(c->bvh.nodes); cudaFree(c->bvh.tris); cudaFree(c->bvh.triInfo);
+  cudaFree(c->bvh.nodes); cudaFree(c->bvh.tris); cudaFree(c->bvh.triInfo); cudaFree(c->bvh.triShade);
   c->dVerts = nullptr; c->dIdx = nullptr; c->dGeo = nullptr; c->dInst = nullptr; c->dInstTriOffset = nullptr;
   c->dMat = nullptr; c->dLights = nullptr; c->dTexDescs = nullptr;
   c->bvh = BvhResult{};
@@ -492,6 +492,7 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
   v.nodes        = ctx->bvh.nodes;
   v.tris         = ctx->bvh.tris;
   v.triInfo      = ctx->bvh.triInfo;
+  v.triShade     = ctx->bvh.triShade;
   v.instances    = ctx->dInst;
   v.geoInfo      = ctx->dGeo;
   v.materials    = ctx->dMat;
@@ -715,9 +716,11 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
     return VKRT_OK;
   int fif = o.frames_in_flight;
   if(fif <= 0)
-    fif = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(4u << 20) / nLocal));
-  fif = std::min(fif, num_frames);
+    fif = (int)std::max<size_t>(1, std::min<size_t>(64, (size_t)(32u << 20) / nLocal));  // ~32 M paths (5.4 GB of wavefront state): amortises the latency floor of thin late bounces
+  // the wavefront is sized for the full batch even when this call renders fewer frames, so that a later, longer
+  // call does not reallocate gigabytes in the middle of a render (grow-only)
   rc  = ensureWavefront(ctx, (size_t)nLocal * fif);
+  fif = std::min(fif, num_frames);
   if(rc != VKRT_OK) return rc;
 
   TraceStats* dstats = ctx->dStats;

@@ -47,7 +47,7 @@ VKRT_D float GTR1(float NdotH, float a)
     return kInvPi;
   float a2 = a * a;
   float t  = 1.0f + (a2 - 1.0f) * NdotH * NdotH;
-  return (a2 - 1.0f) / (kPi * logf(a2) * t);
+  return (a2 - 1.0f) / (kPi * m_logf(a2) * t);
 }
 VKRT_D float GTR2(float NdotH, float a)
 {
@@ -87,17 +87,17 @@ VKRT_D float3 SampleGTR1(float rgh, float r1, float r2)
   float a        = fmaxf(0.001f, rgh);
   float a2       = a * a;
   float phi      = r1 * kTwoPi;
-  float cosTheta = sqrtf((1.0f - powf(a2, 1.0f - r1)) / (1.0f - a2));
+  float cosTheta = sqrtf((1.0f - m_powf(a2, 1.0f - r1)) / (1.0f - a2));
   float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
-  float sinPhi = sinf(phi), cosPhi = cosf(phi);
+  float sinPhi = m_sinf(phi), cosPhi = m_cosf(phi);
   (void)r2;
   return f3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
 }
 VKRT_D float3 SampleGTR2Aniso(float ax, float ay, float r1, float r2)
 {
   float phi      = r1 * kTwoPi;
-  float sinPhi   = ay * sinf(phi);
-  float cosPhi   = ax * cosf(phi);
+  float sinPhi   = ay * m_sinf(phi);
+  float cosPhi   = ax * m_cosf(phi);
   float tanTheta = sqrtf(r2 / (1 - r2));
   return f3(tanTheta * cosPhi, tanTheta * sinPhi, 1.0f);
 }
@@ -107,7 +107,7 @@ VKRT_D float3 SampleGTR2(float rgh, float r1, float r2)
   float phi      = r1 * kTwoPi;
   float cosTheta = sqrtf((1.0f - r2) / (1.0f + (a * a - 1.0f) * r2));
   float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
-  float sinPhi = sinf(phi), cosPhi = cosf(phi);
+  float sinPhi = m_sinf(phi), cosPhi = m_cosf(phi);
   return f3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
 }
 VKRT_D float3 CosineSampleHemisphere(float r1, float r2)
@@ -115,8 +115,8 @@ VKRT_D float3 CosineSampleHemisphere(float r1, float r2)
   float  r   = sqrtf(r1);
   float  phi = kTwoPi * r2;
   float3 dir;
-  dir.x = r * cosf(phi);
-  dir.y = r * sinf(phi);
+  dir.x = r * m_cosf(phi);
+  dir.y = r * m_sinf(phi);
   dir.z = sqrtf(fmaxf(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
   return dir;
 }
@@ -124,7 +124,7 @@ VKRT_D float3 UniformSampleHemisphere(float r1, float r2)
 {
   float r   = sqrtf(fmaxf(0.0f, 1.0f - r1 * r1));
   float phi = kTwoPi * r2;
-  return f3(r * cosf(phi), r * sinf(phi), r1);
+  return f3(r * m_cosf(phi), r * m_sinf(phi), r1);
 }
 
 // ----------------------------------------------------------------------------- Disney lobes
@@ -343,7 +343,7 @@ VKRT_D float3 DisneyEval(const ShadeMat& m, const ShadeFrame& fr, float3 V, floa
 
 // ----------------------------------------------------------------------------- glTF model
 // pbr_gltf.glsl:36-112
-VKRT_D float  pow5(float x) { return powf(x, 5.0f); }
+VKRT_D float  pow5(float x) { return m_powf(x, 5.0f); }
 VKRT_D float3 F_Schlick3(float3 f0, float3 f90, float VdotH) { return f0 + (f90 - f0) * pow5(clampf(1.0f - VdotH, 0.0f, 1.0f)); }
 VKRT_D float  F_Schlick1(float f0, float f90, float VdotH) { return f0 + (f90 - f0) * pow5(clampf(1.0f - VdotH, 0.0f, 1.0f)); }
 VKRT_D float  V_GGX(float NdotL, float NdotV, float alphaRoughness)
@@ -388,7 +388,7 @@ VKRT_D float3 GgxSampling(float specularAlpha, float r1, float r2)
   float phi      = r1 * 2.0f * kPi;
   float cosTheta = sqrtf((1.0f - r2) / (1.0f + (specularAlpha * specularAlpha - 1.0f) * r2));
   float sinTheta = clampf(sqrtf(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
-  float sinPhi = sinf(phi), cosPhi = cosf(phi);
+  float sinPhi = m_sinf(phi), cosPhi = m_cosf(phi);
   return f3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
 }
 // pbr_gltf.glsl:203-219

@@ -44,7 +44,7 @@ __device__ __forceinline__ uint64_t expandBits21(uint32_t v)
 // ---- 1. flatten ----------------------------------------------------------------------
 __global__ void flattenKernel(const InstanceXform* __restrict__ inst, const uint32_t* __restrict__ instTriOffset, uint32_t numInst,
                               const InstanceData* __restrict__ geo, uint32_t numTris, float4* __restrict__ wtri,
-                              uint2* __restrict__ triInfo, uint32_t* __restrict__ boundsOrdered /*6*/)
+                              uint2* __restrict__ triInfo, uint4* __restrict__ triShade, uint32_t* __restrict__ boundsOrdered /*6*/)
 {
   uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x;
   float3   c   = f3(0.f);
@@ -76,6 +76,16 @@ __global__ void flattenKernel(const InstanceXform* __restrict__ inst, const uint
     wtri[3ull * gid + 1] = f4(v1, __uint_as_float(gid));
     wtri[3ull * gid + 2] = f4(v2, 0.f);
     triInfo[gid]         = make_uint2(lo, prim);
+    // per-triangle shading record: the three 32-byte vertices + {instance, material}; one dependent load from the hit
+    // instead of triInfo -> instance -> geometry -> indices -> vertices
+    {
+      const uint4* v4 = reinterpret_cast<const uint4*>(vtx);
+      uint4*       ts = triShade + 7ull * gid;
+      ts[0] = v4[2ull * idx[0]]; ts[1] = v4[2ull * idx[0] + 1];
+      ts[2] = v4[2ull * idx[1]]; ts[3] = v4[2ull * idx[1] + 1];
+      ts[4] = v4[2ull * idx[2]]; ts[5] = v4[2ull * idx[2] + 1];
+      ts[6] = make_uint4(lo, (uint32_t)max(0, g.materialIndex), I.flags, prim);
+    }
     float3 lo3 = f3(fminf(v0.x, fminf(v1.x, v2.x)), fminf(v0.y, fminf(v1.y, v2.y)), fminf(v0.z, fminf(v1.z, v2.z)));
     float3 hi3 = f3(fmaxf(v0.x, fmaxf(v1.x, v2.x)), fmaxf(v0.y, fmaxf(v1.y, v2.y)), fmaxf(v0.z, fmaxf(v1.z, v2.z)));
     c          = (lo3 + hi3) * 0.5f;
@@ -347,6 +357,7 @@ bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* d
   CK(cudaMalloc(&out.nodes, sizeof(float4) * 4ull * numNodes));
   CK(cudaMalloc(&out.tris, sizeof(float4) * 3ull * (numTris ? numTris : 1)));
   CK(cudaMalloc(&out.triInfo, sizeof(uint2) * (numTris ? numTris : 1)));
+  CK(cudaMalloc(&out.triShade, sizeof(uint4) * 7ull * (numTris ? numTris : 1)));
   out.numNodes = numNodes;
   out.numTris  = numTris;
   if(numTris == 0)
@@ -374,7 +385,7 @@ bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* d
     CK(cudaMemsetAsync(collapsed, 0, 4 * n, stream));
     CK(cudaMemsetAsync(maxDepthDev, 0, 4, stream));
     uint32_t grid = (uint32_t)((n + B - 1) / B);
-    flattenKernel<<<grid, B, 0, stream>>>(dInst, dInstTriOffset, numInst, dGeo, numTris, wtri, out.triInfo, bounds);
+    flattenKernel<<<grid, B, 0, stream>>>(dInst, dInstTriOffset, numInst, dGeo, numTris, wtri, out.triInfo, out.triShade, bounds);
     mortonKernel<<<grid, B, 0, stream>>>(wtri, numTris, bounds, keysA, valsA);
     size_t tempBytes = 0;
     cub::DoubleBuffer<uint64_t> dk(keysA, keysB);
@@ -403,7 +414,7 @@ fail:
   cudaFree(wtri); cudaFree(bounds); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB); cudaFree(cubTemp);
   cudaFree(children); cudaFree(ranges); cudaFree(parentInner); cudaFree(parentLeaf); cudaFree(flags); cudaFree(nodeDepth);
   cudaFree(maxDepthDev); cudaFree(leafBox); cudaFree(nodeBox); cudaFree(nodeCost); cudaFree(collapsed);
-  cudaFree(out.nodes); cudaFree(out.tris); cudaFree(out.triInfo);
+  cudaFree(out.nodes); cudaFree(out.tris); cudaFree(out.triInfo); cudaFree(out.triShade);
   out = BvhResult{};
   return false;
 }

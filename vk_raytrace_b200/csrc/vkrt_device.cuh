@@ -45,6 +45,7 @@ struct SceneView
   const float4* nodes;     // 4 per node
   const float4* tris;      // 3 per triangle, leaf order
   const uint2*  triInfo;   // by flattened triangle id: {node(instance), prim}
+  const uint4*  triShade;  // by flattened triangle id: 3 x VertexAttributes (6 x uint4) + {instance, material, flags, prim}
   // shading
   const InstanceXform*     instances;
   const InstanceData*      geoInfo;    // per primMesh: reference layout, CUDA pointers

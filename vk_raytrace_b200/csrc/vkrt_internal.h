@@ -17,6 +17,7 @@ struct BvhResult
   float4*  nodes    = nullptr;
   float4*  tris     = nullptr;
   uint2*   triInfo  = nullptr;
+  uint4*   triShade = nullptr;  // 7 x uint4 per flattened triangle
   uint32_t numNodes = 0;
   uint32_t numTris  = 0;
   int      maxDepth = 0;

@@ -51,7 +51,11 @@ VKRT_HD float  dot(float3 a, float3 b) { return (a.x * b.x + a.y * b.y) + a.z * 
 VKRT_HD float  dot(float2 a, float2 b) { return a.x * b.x + a.y * b.y; }
 VKRT_HD float3 cross(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 VKRT_HD float  length(float3 a) { return sqrtf(dot(a, a)); }
+#if defined(__CUDA_ARCH__) && defined(VKRT_COMPACT_MATH)
+__device__ __noinline__ float3 normalize(float3 a)
+#else
 VKRT_HD float3 normalize(float3 a)
+#endif
 {
   float inv = 1.0f / sqrtf(dot(a, a));
   return a * inv;
@@ -65,10 +69,27 @@ VKRT_HD float  smoothstepf(float e0, float e1, float x)
   float t = clampf((x - e0) / (e1 - e0), 0.0f, 1.0f);
   return t * t * (3.0f - 2.0f * t);
 }
+// Transcendentals behind one call site each: the CUDA libm bodies are 50-200 instructions (sinf/cosf carry a
+// Payne-Hanek slow path), and the shade kernel uses dozens of them -- inlining every one blew the kernel up to
+// 16k instructions and made it instruction-fetch bound (profiles/README.md).  Results are unchanged.
+#if defined(__CUDA_ARCH__) && defined(VKRT_COMPACT_MATH)
+#define VKRT_MATHFN __device__ __noinline__
+#else
+#define VKRT_MATHFN VKRT_HD
+#endif
+VKRT_MATHFN float m_sinf(float x) { return sinf(x); }
+VKRT_MATHFN float m_cosf(float x) { return cosf(x); }
+VKRT_MATHFN float m_powf(float x, float y) { return powf(x, y); }
+VKRT_MATHFN float m_expf(float x) { return expf(x); }
+VKRT_MATHFN float m_logf(float x) { return logf(x); }
+VKRT_MATHFN float m_acosf(float x) { return acosf(x); }
+VKRT_MATHFN float m_asinf(float x) { return asinf(x); }
+VKRT_MATHFN float m_atan2f(float y, float x) { return atan2f(y, x); }
+
 VKRT_HD float3 clamp3(float3 v, float lo, float hi) { return f3(clampf(v.x, lo, hi), clampf(v.y, lo, hi), clampf(v.z, lo, hi)); }
-VKRT_HD float3 pow3(float3 v, float e) { return f3(powf(v.x, e), powf(v.y, e), powf(v.z, e)); }
-VKRT_HD float3 exp3(float3 v) { return f3(expf(v.x), expf(v.y), expf(v.z)); }
-VKRT_HD float3 log3(float3 v) { return f3(logf(v.x), logf(v.y), logf(v.z)); }
+VKRT_HD float3 pow3(float3 v, float e) { return f3(m_powf(v.x, e), m_powf(v.y, e), m_powf(v.z, e)); }
+VKRT_HD float3 exp3(float3 v) { return f3(m_expf(v.x), m_expf(v.y), m_expf(v.z)); }
+VKRT_HD float3 log3(float3 v) { return f3(m_logf(v.x), m_logf(v.y), m_logf(v.z)); }
 VKRT_HD float3 sqrt3(float3 v) { return f3(sqrtf(v.x), sqrtf(v.y), sqrtf(v.z)); }
 VKRT_HD float3 floor3(float3 v) { return f3(floorf(v.x), floorf(v.y), floorf(v.z)); }
 VKRT_HD float  maxcomp(float3 v) { return fmaxf(v.x, fmaxf(v.y, v.z)); }
@@ -168,7 +189,11 @@ VKRT_HD float short_to_floatm11(int v)
 {
   return (v >= 0) ? (u2f(0x3F800000u | (uint32_t(v) << 8)) - 1.0f) : (u2f(0xBF800000u | (uint32_t(-v) << 8)) + 1.0f);
 }
+#if defined(__CUDA_ARCH__) && defined(VKRT_COMPACT_MATH)
+__device__ __noinline__ float3 decompress_unit_vec(uint32_t packed)
+#else
 VKRT_HD float3 decompress_unit_vec(uint32_t packed)
+#endif
 {
   if(packed == ~0u)
     return f3(3.402823466e+38f);
@@ -202,8 +227,8 @@ VKRT_HD float4 unpackUnorm4x8(uint32_t p)
 // shaders/common.glsl:67-113
 VKRT_HD float2 GetSphericalUv(float3 v)
 {
-  float gamma = asinf(-v.y);
-  float theta = atan2f(v.z, v.x);
+  float gamma = m_asinf(-v.y);
+  float theta = m_atan2f(v.z, v.x);
   return f2(theta * kInvPi * 0.5f + 0.5f, gamma * kInvPi + 0.5f);
 }
 VKRT_HD void CreateCoordinateSystem(float3 N, float3& Nt, float3& Nb)

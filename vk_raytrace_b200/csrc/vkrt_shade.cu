@@ -9,6 +9,8 @@
 // The megakernel's `for depth` loop becomes one trace + one shade launch per bounce;
 // every path carries its RNG seed and consumes draws in the reference's order
 // (SURVEY.md App. B), so results do not depend on scheduling.
+#define VKRT_COMPACT_MATH 1
+#define VKRT_COMPACT_TEXTURE 1
 #include "vkrt_device.cuh"
 #include "vkrt_texture.cuh"
 #include "vkrt_bsdf.cuh"
@@ -17,7 +19,8 @@
 
 namespace vkrt {
 
-constexpr int kShadeBlock = 128;
+constexpr int kShadeBlock     = 320;
+constexpr int kShadeMinBlocks = 2;  // <= 96 registers: 640 threads per SM; large CTAs so that the phase barriers keep many warps in step
 
 // ---- ray generation: pathtrace.comp:97 / pathtrace.rgen:72 + pathtrace.glsl:348-376 -------------------
 __global__ void __launch_bounds__(256) raygenKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(256) raygenKernel(const __grid_constant__ Scen
   float  cam_r2      = rnd(seed) * cam.aperture;
   float4 cam_right   = mulMV(cam.viewInverse, f4(1, 0, 0, 0));
   float4 cam_up      = mulMV(cam.viewInverse, f4(0, 1, 0, 0));
-  float3 aperturePos = (cosf(cam_r1) * f3(cam_right) + sinf(cam_r1) * f3(cam_up)) * sqrtf(cam_r2);
+  float3 aperturePos = (m_cosf(cam_r1) * f3(cam_right) + m_sinf(cam_r1) * f3(cam_up)) * sqrtf(cam_r2);
   float3 rayDir      = normalize(focalPoint - aperturePos);
 
   wf.rayO[p]     = f4(f3(origin) + aperturePos, kInfinity);
@@ -98,15 +101,10 @@ struct HitGeom
 VKRT_D HitGeom loadHitGeom(const SceneView& sc, uint32_t triId, float bu, float bv)
 {
   HitGeom g;
-  const uint2          info = __ldg(&sc.triInfo[triId]);
-  const InstanceXform& I    = sc.instances[info.x];
-  const InstanceData   geo  = sc.geoInfo[I.primMesh];
-  const uint32_t*      idx  = reinterpret_cast<const uint32_t*>(geo.indexAddress) + 3ull * info.y;
-  const uint4*         vtx  = reinterpret_cast<const uint4*>(geo.vertexAddress);  // 32-B vertices as 2 x 16 B
-  const uint32_t       i0 = __ldg(idx), i1 = __ldg(idx + 1), i2 = __ldg(idx + 2);
-  const uint4 a0 = __ldg(&vtx[2ull * i0]), a1 = __ldg(&vtx[2ull * i0 + 1]);
-  const uint4 b0 = __ldg(&vtx[2ull * i1]), b1 = __ldg(&vtx[2ull * i1 + 1]);
-  const uint4 c0 = __ldg(&vtx[2ull * i2]), c1 = __ldg(&vtx[2ull * i2 + 1]);
+  const uint4* ts = sc.triShade + 7ull * triId;
+  const uint4  a0 = __ldg(ts + 0), a1 = __ldg(ts + 1), b0 = __ldg(ts + 2), b1 = __ldg(ts + 3), c0 = __ldg(ts + 4), c1 = __ldg(ts + 5);
+  const uint4  meta = __ldg(ts + 6);  // {instance, material, flags, prim}
+  const InstanceXform& I = sc.instances[meta.x];
   // VertexAttributes: {pos.xyz, normal | uv.xy, tangent, color}
   const float3 bary = f3(1.0f - bu - bv, bu, bv);
   const float3 pos0 = f3(__uint_as_float(a0.x), __uint_as_float(a0.y), __uint_as_float(a0.z));
@@ -135,7 +133,7 @@ VKRT_D HitGeom loadHitGeom(const SceneView& sc, uint32_t triId, float bu, float 
 
   const float4 col = unpackUnorm4x8(a1.w) * bary.x + unpackUnorm4x8(b1.w) * bary.y + unpackUnorm4x8(c1.w) * bary.z;
   g.color          = f3(col);
-  g.matIndex       = (uint32_t)max(0, geo.materialIndex);
+  g.matIndex       = meta.y;
   g.normal         = worldNormal;
   if(dot(g.normal, wgeomNormal) <= 0)
     g.normal *= -1.0f;
@@ -236,7 +234,7 @@ VKRT_D float rangeAttenuation(float range, float distance)
 {
   if(range <= 0.0f)
     return 1.0f;
-  return fmaxf(fminf(1.0f - powf(distance / range, 4.0f), 1.0f), 0.0f) / powf(distance, 2.0f);
+  return fmaxf(fminf(1.0f - m_powf(distance / range, 4.0f), 1.0f), 0.0f) / m_powf(distance, 2.0f);
 }
 VKRT_D float spotAttenuation(float3 pointToLight, float3 spotDirection, float outerConeCos, float innerConeCos)
 {
@@ -251,7 +249,7 @@ VKRT_D float spotAttenuation(float3 pointToLight, float3 spotDirection, float ou
 }
 
 // ---- env_sampling.glsl:38-135 -------------------------------------------------------------------------
-VKRT_D float3 environmentSample(const SceneView& sc, float3 xi, float3& toLight, float& pdf)
+__device__ __noinline__ float3 environmentSample(const SceneView& sc, float3 xi, float3& toLight, float& pdf)
 {
   const uint32_t width = (uint32_t)sc.envW, height = (uint32_t)sc.envH;
   const uint32_t size  = width * height;
@@ -274,13 +272,13 @@ VKRT_D float3 environmentSample(const SceneView& sc, float3 xi, float3& toLight,
   const uint32_t py = envIdx / width;
   const float    u        = (float)((float)px + xi.y) / (float)width;
   const float    phi      = u * (2.0f * kPi) - kPi;
-  const float    sinPhi   = sinf(phi);
-  const float    cosPhi   = cosf(phi);
+  const float    sinPhi   = m_sinf(phi);
+  const float    cosPhi   = m_cosf(phi);
   const float    stepTheta = kPi / (float)height;
   const float    theta0    = (float)py * stepTheta;
-  const float    cosTheta  = cosf(theta0) * (1.0f - xi.z) + cosf(theta0 + stepTheta) * xi.z;
-  const float    theta     = acosf(cosTheta);
-  const float    sinTheta  = sinf(theta);
+  const float    cosTheta  = m_cosf(theta0) * (1.0f - xi.z) + m_cosf(theta0 + stepTheta) * xi.z;
+  const float    theta     = m_acosf(cosTheta);
+  const float    sinTheta  = m_sinf(theta);
   const float    v         = theta * kInvPi;
   toLight = f3(cosPhi * sinTheta, cosTheta, sinPhi * sinTheta);
   return sampleEnv(sc, f2(u, v));
@@ -295,176 +293,198 @@ struct ShadeOut
   uint32_t shSeed;
 };
 
-// One bounce of pathtrace.glsl:199-340 for one path.  Returns through `radiance`, `throughput`,
-// `absorption`, `seed` (all inout) and `out`.
-VKRT_D void shadeBounce(const SceneView& sc, const FrameParams& fp, float3 rayO, float3 rayD, float4 hit, float3& radiance,
-                        float3& throughput, float3& absorption, uint32_t& seed, ShadeOut& out)
+// One bounce of pathtrace.glsl:199-340 for one path, cut into three phases so that the block can re-synchronise
+// between them: the bounce is ~9k instructions, far beyond the instruction cache, and warps that drift apart
+// each stream their own copy of the code from L2 (ncu: "no instruction" was the top stall).  With a barrier
+// between phases all warps of a block fetch the same region together.
+struct BounceState
 {
-  out.wantNext   = false;
-  out.wantShadow = false;
+  float3     rayD, position, radiance, throughput, absorption;
+  float      hitT;
+  uint32_t   seed;
+  ShadeMat   m;
+  ShadeFrame fr;
+  float3     lightDir, vcontrib;
+  float      lightDist;
+  bool       visible;
+};
+
+// Phase A: miss handling, shading state, material, debug views, emission/absorption (pathtrace.glsl:204-274).
+// Returns false when the path ends here.
+VKRT_D bool bouncePhaseSurface(const SceneView& sc, const FrameParams& fp, float4 hit, BounceState& b)
+{
   const int dbg      = fp.state.debugging_mode;
   const int depth    = fp.depth;
   const int maxDepth = fp.state.maxDepth;
-
-  // ---- miss: pathtrace.glsl:204-228 ----
   if(hit.x == kInfinity)
   {
     if(dbg != VKRT_DBG_NONE)
     {
-      if(depth != maxDepth - 1) { radiance = f3(0.f); return; }
-      if(dbg == VKRT_DBG_RADIANCE) return;
-      else if(dbg == VKRT_DBG_WEIGHT) { radiance = throughput; return; }
-      else if(dbg == VKRT_DBG_RAYDIR) { radiance = (rayD + f3(1.f)) * 0.5f; return; }
+      if(depth != maxDepth - 1) { b.radiance = f3(0.f); return false; }
+      if(dbg == VKRT_DBG_RADIANCE) return false;
+      else if(dbg == VKRT_DBG_WEIGHT) { b.radiance = b.throughput; return false; }
+      else if(dbg == VKRT_DBG_RAYDIR) { b.radiance = (b.rayD + f3(1.f)) * 0.5f; return false; }
     }
     float3 env;
     if(sc.sunsky.in_use == 1)
-      env = sky::sunAndSky(sc.sunsky, rayD);
+      env = sky::sunAndSky(sc.sunsky, b.rayD);
     else
-      env = sampleEnv(sc, GetSphericalUv(rayD));
-    radiance = radiance + (env * fp.state.hdrMultiplier * throughput);
-    return;
+      env = sampleEnv(sc, GetSphericalUv(b.rayD));
+    b.radiance = b.radiance + (env * fp.state.hdrMultiplier * b.throughput);
+    return false;
   }
-
   const HitGeom g = loadHitGeom(sc, __float_as_uint(hit.w), hit.y, hit.z);
-  ShadeMat   m;
-  ShadeFrame fr;
-  float2     texCoord;
-  resolveMaterial(sc, g, rayD, m, fr, texCoord);
-  m.albedo *= g.color;
-
-  // ---- debug views: pathtrace.glsl:61-83,255-256 ----
+  float2        texCoord;
+  resolveMaterial(sc, g, b.rayD, b.m, b.fr, texCoord);
+  b.m.albedo *= g.color;
+  b.position = g.position;
+  b.hitT     = hit.x;
   if(dbg != VKRT_DBG_NONE && dbg < VKRT_DBG_RADIANCE)
   {
     switch(dbg)
     {
-      case VKRT_DBG_METALLIC: radiance = f3(m.metallic); break;
-      case VKRT_DBG_NORMAL: radiance = (fr.normal + f3(1.f)) * .5f; break;
-      case VKRT_DBG_BASECOLOR: radiance = m.albedo; break;
-      case VKRT_DBG_EMISSIVE: radiance = m.emission; break;
-      case VKRT_DBG_ALPHA: radiance = f3(m.alpha); break;
-      case VKRT_DBG_ROUGHNESS: radiance = f3(m.roughness); break;
-      case VKRT_DBG_TEXCOORD: radiance = f3(texCoord.x, texCoord.y, 0.f); break;
-      case VKRT_DBG_TANGENT: radiance = (fr.tangent + f3(1.f)) * .5f; break;
-      default: radiance = f3(1000.f, 0.f, 0.f); break;
+      case VKRT_DBG_METALLIC: b.radiance = f3(b.m.metallic); break;
+      case VKRT_DBG_NORMAL: b.radiance = (b.fr.normal + f3(1.f)) * .5f; break;
+      case VKRT_DBG_BASECOLOR: b.radiance = b.m.albedo; break;
+      case VKRT_DBG_EMISSIVE: b.radiance = b.m.emission; break;
+      case VKRT_DBG_ALPHA: b.radiance = f3(b.m.alpha); break;
+      case VKRT_DBG_ROUGHNESS: b.radiance = f3(b.m.roughness); break;
+      case VKRT_DBG_TEXCOORD: b.radiance = f3(texCoord.x, texCoord.y, 0.f); break;
+      case VKRT_DBG_TANGENT: b.radiance = (b.fr.tangent + f3(1.f)) * .5f; break;
+      default: b.radiance = f3(1000.f, 0.f, 0.f); break;
     }
-    return;
+    return false;
   }
-  if(m.unlit)
+  if(b.m.unlit)
   {
-    radiance = radiance + m.albedo * throughput;
-    return;
+    b.radiance = b.radiance + b.m.albedo * b.throughput;
+    return false;
   }
-  if(dot(fr.normal, fr.ffnormal) > 0.0f)
-    absorption = f3(0.0f);
-  radiance += m.emission * throughput;
-  throughput *= exp3(-absorption * hit.x);
+  if(dot(b.fr.normal, b.fr.ffnormal) > 0.0f)
+    b.absorption = f3(0.0f);
+  b.radiance += b.m.emission * b.throughput;
+  b.throughput *= exp3(-b.absorption * b.hitT);
+  return true;
+}
 
-  // ---- DirectLight: pathtrace.glsl:97-188 ----
-  const float3 V = -rayD;
+// Phase B: DirectLight (pathtrace.glsl:97-188).
+template <int PBR>
+VKRT_D void bouncePhaseLight(const SceneView& sc, const FrameParams& fp, BounceState& b)
+{
+  const float3 V = -b.rayD;
   float3 lightContrib, lightDir;
   float  lightPdf;
   float  lightDist = 1e32f;
   bool   isLight   = false;
-  bool   visible   = false;
-  float3 vcontrib  = f3(0.f);
+  b.visible  = false;
+  b.vcontrib = f3(0.f);
+  const float pSelectLight = fp.state.hdrMultiplier > 0.0f ? 0.5f : 1.0f;
+  const int   nbLights     = sc.camera.nbLights;
+  if(nbLights != 0 && rnd(b.seed) <= pSelectLight)
   {
-    const float pSelectLight = fp.state.hdrMultiplier > 0.0f ? 0.5f : 1.0f;
-    const int   nbLights     = sc.camera.nbLights;
-    if(nbLights != 0 && rnd(seed) <= pSelectLight)
+    isLight = true;
+    int lightIndex = (int)fminf(rnd(b.seed) * (float)nbLights, (float)nbLights);
+    lightIndex     = min(lightIndex, nbLights - 1);  // memory safety only; unreachable for rand < 1
+    const Light& light = sc.lights[lightIndex];
+    const float3 ldir  = f3(light.direction[0], light.direction[1], light.direction[2]);
+    float3 pointToLight = -ldir;
+    float  rangeAtt = 1.0f, spotAtt = 1.0f;
+    if(light.type != VKRT_LIGHT_DIRECTIONAL)
+      pointToLight = f3(light.position[0], light.position[1], light.position[2]) - b.position;
+    lightDist = length(pointToLight);
+    if(light.type != VKRT_LIGHT_DIRECTIONAL)
+      rangeAtt = rangeAttenuation(light.range, lightDist);
+    if(light.type == VKRT_LIGHT_SPOT)
+      spotAtt = spotAttenuation(pointToLight, ldir, light.outerConeCos, light.innerConeCos);
+    lightContrib = rangeAtt * spotAtt * light.intensity * f3(light.color[0], light.color[1], light.color[2]);
+    lightDir     = normalize(pointToLight);
+    lightPdf     = 1.0f;
+  }
+  else
+  {
+    if(sc.sunsky.in_use == 1)
     {
-      isLight = true;
-      int lightIndex = (int)fminf(rnd(seed) * (float)nbLights, (float)nbLights);
-      lightIndex     = min(lightIndex, nbLights - 1);  // memory safety only; unreachable for rand < 1
-      const Light& light = sc.lights[lightIndex];
-      const float3 ldir  = f3(light.direction[0], light.direction[1], light.direction[2]);
-      float3 pointToLight = -ldir;
-      float  rangeAtt = 1.0f, spotAtt = 1.0f;
-      if(light.type != VKRT_LIGHT_DIRECTIONAL)
-        pointToLight = f3(light.position[0], light.position[1], light.position[2]) - g.position;
-      lightDist = length(pointToLight);
-      if(light.type != VKRT_LIGHT_DIRECTIONAL)
-        rangeAtt = rangeAttenuation(light.range, lightDist);
-      if(light.type == VKRT_LIGHT_SPOT)
-        spotAtt = spotAttenuation(pointToLight, ldir, light.outerConeCos, light.innerConeCos);
-      lightContrib = rangeAtt * spotAtt * light.intensity * f3(light.color[0], light.color[1], light.color[2]);
-      lightDir     = normalize(pointToLight);
-      lightPdf     = 1.0f;
+      const float  sunRadius = (0.00465f * 10.0f) * sc.sunsky.sun_disk_scale;
+      const float3 sd = f3(sc.sunsky.sun_direction[0], sc.sunsky.sun_direction[1], sc.sunsky.sun_direction[2]);
+      float3 T, B;
+      CreateCoordinateSystem(sd, T, B);
+      float3 dir;
+      dir.x    = rnd(b.seed) * sunRadius;
+      dir.y    = rnd(b.seed) * sunRadius;
+      dir.z    = sqrtf(fmaxf(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
+      lightDir = normalize(T * dir.x + B * dir.y + sd * dir.z);
+      lightContrib = sky::sunAndSky(sc.sunsky, lightDir);
+      lightPdf = 0.5f;
     }
     else
     {
-      if(sc.sunsky.in_use == 1)
-      {
-        const float  sunRadius = (0.00465f * 10.0f) * sc.sunsky.sun_disk_scale;
-        const float3 sd = f3(sc.sunsky.sun_direction[0], sc.sunsky.sun_direction[1], sc.sunsky.sun_direction[2]);
-        float3 T, B;
-        CreateCoordinateSystem(sd, T, B);
-        float3 dir;
-        dir.x    = rnd(seed) * sunRadius;
-        dir.y    = rnd(seed) * sunRadius;
-        dir.z    = sqrtf(fmaxf(0.0f, 1.0f - dir.x * dir.x - dir.y * dir.y));
-        lightDir = normalize(T * dir.x + B * dir.y + sd * dir.z);
-        lightContrib = sky::sunAndSky(sc.sunsky, lightDir);
-        lightPdf = 0.5f;
-      }
-      else
-      {
-        float a = rnd(seed), b = rnd(seed), c = rnd(seed);
-        lightContrib = environmentSample(sc, f3(a, b, c), lightDir, lightPdf);
-      }
-      lightContrib *= fp.state.hdrMultiplier;
+      float r0 = rnd(b.seed), r1 = rnd(b.seed), r2 = rnd(b.seed);
+      lightContrib = environmentSample(sc, f3(r0, r1, r2), lightDir, lightPdf);
     }
-    if(fr.isSubsurface || dot(lightDir, fr.ffnormal) > 0.0f)
-    {
-      float  bpdf = 0.f;
-      float3 f = (fp.state.pbrMode == 0) ? DisneyEval(m, fr, V, fr.ffnormal, lightDir, bpdf) : PbrEval(m, fr, V, fr.ffnormal, lightDir, bpdf);
-      float  misWeight = isLight ? 1.0f : fmaxf(0.0f, powerHeuristic(lightPdf, bpdf));
-      vcontrib = misWeight * f * fabsf(dot(lightDir, fr.ffnormal)) * lightContrib / lightPdf;
-      visible  = true;
-    }
+    lightContrib *= fp.state.hdrMultiplier;
   }
-  vcontrib *= throughput;
+  if(b.fr.isSubsurface || dot(lightDir, b.fr.ffnormal) > 0.0f)
+  {
+    float  bpdf = 0.f;
+    float3 f = (PBR == 0) ? DisneyEval(b.m, b.fr, V, b.fr.ffnormal, lightDir, bpdf) : PbrEval(b.m, b.fr, V, b.fr.ffnormal, lightDir, bpdf);
+    float  misWeight = isLight ? 1.0f : fmaxf(0.0f, powerHeuristic(lightPdf, bpdf));
+    b.vcontrib = misWeight * f * fabsf(dot(lightDir, b.fr.ffnormal)) * lightContrib / lightPdf;
+    b.visible  = true;
+  }
+  b.vcontrib *= b.throughput;
+  b.lightDir  = lightDir;
+  b.lightDist = lightDist;
+}
 
-  // ---- BSDF sample: pathtrace.glsl:281-296 ----
+// Phase C: BSDF sample, next ray, shadow ray, Russian roulette (pathtrace.glsl:281-340).
+template <int PBR>
+VKRT_D void bouncePhaseSample(const SceneView& sc, const FrameParams& fp, BounceState& b, ShadeOut& out)
+{
+  const int dbg      = fp.state.debugging_mode;
+  const int depth    = fp.depth;
+  const int maxDepth = fp.state.maxDepth;
+  const float3 V = -b.rayD;
   float3 L   = f3(0.f);
   float  pdf = 0.f;
-  float3 f   = (fp.state.pbrMode == 0) ? DisneySample(m, fr, V, fr.ffnormal, L, pdf, seed) : PbrSample(m, fr, V, fr.ffnormal, L, pdf, seed);
+  float3 f   = (PBR == 0) ? DisneySample(b.m, b.fr, V, b.fr.ffnormal, L, pdf, b.seed) : PbrSample(b.m, b.fr, V, b.fr.ffnormal, L, pdf, b.seed);
 
-  if(dot(fr.ffnormal, L) < 0.0f)
-    absorption = -log3(m.attenuationColor) / f3(m.attenuationDistance);
+  if(dot(b.fr.ffnormal, L) < 0.0f)
+    b.absorption = -log3(b.m.attenuationColor) / f3(b.m.attenuationDistance);
 
   if(pdf > 0.0f)
-    throughput *= f * fabsf(dot(fr.ffnormal, L)) / pdf;
+    b.throughput *= f * fabsf(dot(b.fr.ffnormal, L)) / pdf;
   else
     return;  // break: no shadow ray, no RR draw
 
   if(dbg != VKRT_DBG_NONE && (depth == maxDepth - 1))
   {
-    if(dbg == VKRT_DBG_RADIANCE) { radiance = vcontrib; return; }
-    else if(dbg == VKRT_DBG_WEIGHT) { radiance = throughput; return; }
-    else if(dbg == VKRT_DBG_RAYDIR) { radiance = (L + f3(1.f)) * 0.5f; return; }
+    if(dbg == VKRT_DBG_RADIANCE) { b.radiance = b.vcontrib; return; }
+    else if(dbg == VKRT_DBG_WEIGHT) { b.radiance = b.throughput; return; }
+    else if(dbg == VKRT_DBG_RAYDIR) { b.radiance = (L + f3(1.f)) * 0.5f; return; }
   }
 
-  const float rrPcont = fminf(maxcomp(throughput) * fr.eta * fr.eta + 0.001f, 0.95f);
+  const float rrPcont = fminf(maxcomp(b.throughput) * b.fr.eta * b.fr.eta + 0.001f, 0.95f);
 
   out.nextD = L;
-  out.nextO = OffsetRay(g.position, dot(L, fr.ffnormal) > 0 ? fr.ffnormal : -fr.ffnormal);
+  out.nextO = OffsetRay(b.position, dot(L, b.fr.ffnormal) > 0 ? b.fr.ffnormal : -b.fr.ffnormal);
 
-  if(visible)
+  if(b.visible)
   {
     out.wantShadow = true;
-    out.shO = out.nextO; out.shD = lightDir; out.shTmax = lightDist; out.shC = vcontrib; out.shSeed = seed;
+    out.shO = out.nextO; out.shD = b.lightDir; out.shTmax = b.lightDist; out.shC = b.vcontrib; out.shSeed = b.seed;
     // RQ: HitTest draws on prd.seed during the shadow query; RTX: the shadow payload holds a copy
     if(sc.hasNonOpaque && fp.seedMode == VKRT_SEED_RAYQUERY)
-      pcg(seed);
+      pcg(b.seed);
   }
-  if(rnd(seed) >= rrPcont)
+  if(rnd(b.seed) >= rrPcont)
     return;
-  throughput /= rrPcont;
+  b.throughput /= rrPcont;
   out.wantNext = (depth + 1 < maxDepth);
 }
 
-__global__ void __launch_bounds__(kShadeBlock) shadeKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
-                                                           const __grid_constant__ FrameParams fp, TraceStats* stats)
+template <int PBR>
+__global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
+                                                                            const __grid_constant__ FrameParams fp, TraceStats* stats)
 {
   const uint32_t count = wf.counters[0];
   const uint32_t lane  = threadIdx.x & 31u;
@@ -474,21 +494,31 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(const __grid_constant
     const bool     valid = i < count;
     ShadeOut       out;
     out.wantNext = out.wantShadow = false;
-    uint32_t p = 0;
-    uint32_t seed = 0;
+    uint32_t    p = 0;
+    BounceState b;
+    bool        live = false;
     if(valid)
     {
       p = wf.queueCur[i];
-      const float4 ro = wf.rayO[p], rd = wf.rayD[p], h = wf.hit[p];
-      float4       t4 = wf.thr[p], r4 = wf.rad[p], a4 = wf.absb[p];
-      float3       throughput = f3(t4), radiance = f3(r4), absorption = f3(a4);
-      seed = __float_as_uint(t4.w);
+      const float4 rd = wf.rayD[p], h = wf.hit[p];
+      const float4 t4 = wf.thr[p], r4 = wf.rad[p], a4 = wf.absb[p];
+      b.rayD = f3(rd); b.throughput = f3(t4); b.radiance = f3(r4); b.absorption = f3(a4);
+      b.seed = __float_as_uint(t4.w);
       if(sc.hasNonOpaque)
-        pcg(seed);  // the one draw of ClosestHit (see alphaDraw)
-      shadeBounce(sc, fp, f3(ro), f3(rd), h, radiance, throughput, absorption, seed, out);
-      wf.thr[p]  = f4(throughput, __uint_as_float(seed));
-      wf.rad[p]  = f4(radiance, 0.f);
-      wf.absb[p] = f4(absorption, 0.f);
+        pcg(b.seed);  // the one draw of ClosestHit (see alphaDraw)
+      live = bouncePhaseSurface(sc, fp, h, b);
+    }
+    __syncthreads();
+    if(live)
+      bouncePhaseLight<PBR>(sc, fp, b);
+    __syncthreads();
+    if(live)
+      bouncePhaseSample<PBR>(sc, fp, b, out);
+    if(valid)
+    {
+      wf.thr[p]  = f4(b.throughput, __uint_as_float(b.seed));
+      wf.rad[p]  = f4(b.radiance, 0.f);
+      wf.absb[p] = f4(b.absorption, 0.f);
     }
     // warp-aggregated queue appends (all 32 lanes reach this point)
     const unsigned mNext = __ballot_sync(0xffffffffu, out.wantNext);
@@ -506,7 +536,7 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(const __grid_constant
     {
       wf.queueNext[baseNext + __popc(mNext & lt)] = p;
       wf.rayO[p] = f4(out.nextO, kInfinity);
-      wf.rayD[p] = f4(out.nextD, __uint_as_float(seed));
+      wf.rayD[p] = f4(out.nextD, __uint_as_float(b.seed));
     }
     if(out.wantShadow)
     {
@@ -515,6 +545,7 @@ __global__ void __launch_bounds__(kShadeBlock) shadeKernel(const __grid_constant
       wf.shD[k] = f4(out.shD, __uint_as_float(out.shSeed));
       wf.shC[k] = f4(out.shC, __uint_as_float(p));
     }
+    __syncthreads();
   }
   if(stats && blockIdx.x == 0 && threadIdx.x == 0)
     atomicAdd(&stats->closestRays, (unsigned long long)count);
@@ -629,19 +660,28 @@ void launchRaygen(cudaStream_t s, const SceneView& scene, const Wavefront& wf, c
 {
   raygenKernel<<<(wf.numPaths + 255) / 256, 256, 0, s>>>(scene, wf, fp);
 }
-void launchShade(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs)
+template <int PBR>
+static void launchShadeT(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs)
 {
   static int perSM = 0;
   if(!perSM)
   {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shadeKernel, kShadeBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shadeKernel<PBR>, kShadeBlock, 0);
     if(perSM < 1) perSM = 1;
   }
   int grid = numSMs * perSM;
   int need = (int)((wf.numPaths + kShadeBlock - 1) / kShadeBlock);
   if(grid > need) grid = need;
   if(grid < 1) grid = 1;
-  shadeKernel<<<grid, kShadeBlock, 0, s>>>(scene, wf, fp, stats);
+  shadeKernel<PBR><<<grid, kShadeBlock, 0, s>>>(scene, wf, fp, stats);
+}
+void launchShade(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs)
+{
+  // one kernel per BSDF model (RtxState.pbrMode, pathtrace.glsl:40-56): halves the code and register pressure
+  if(fp.state.pbrMode == 0)
+    launchShadeT<0>(s, scene, wf, fp, stats, numSMs);
+  else
+    launchShadeT<1>(s, scene, wf, fp, stats, numSMs);
 }
 void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats) { swapQueuesKernel<<<1, 1, 0, s>>>(wf, stats); }
 void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, int)

@@ -35,7 +35,11 @@ VKRT_D float4 texel8(const TexDesc& t, int x, int y)
   return f4(p.x / 255.0f, p.y / 255.0f, p.z / 255.0f, p.w / 255.0f);
 }
 
+#ifdef VKRT_COMPACT_TEXTURE
+__device__ __noinline__ float4 sampleTexture(const TexDesc& t, float2 uv)
+#else
 VKRT_D float4 sampleTexture(const TexDesc& t, float2 uv)
+#endif
 {
   float u = sanitizeUv(uv.x), v = sanitizeUv(uv.y);
   if(!t.linear)
@@ -55,7 +59,11 @@ VKRT_D float4 sampleTexture(const TexDesc& t, float2 uv)
   return top * (1.0f - ay) + bot * ay;
 }
 
+#ifdef VKRT_COMPACT_TEXTURE
+__device__ __noinline__ float3 sampleEnv(const SceneView& s, float2 uv)
+#else
 VKRT_D float3 sampleEnv(const SceneView& s, float2 uv)
+#endif
 {
   float u = sanitizeUv(uv.x), v = sanitizeUv(uv.y);
   int   w = s.envW, h = s.envH;

@@ -320,6 +320,225 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernel(const __grid_const
 }
 
 
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, 8) traceKernelIfIf(const __grid_constant__ SceneView sc, const __grid_constant__ TraceLaunch L)
+{
+  __shared__ uint32_t s_stack[kStackShared * kTraceBlock];
+  uint32_t* const sstack = &s_stack[threadIdx.x];
+  uint32_t        lstack[kStackLocal];
+  const uint32_t  n    = *L.count;
+  const uint32_t  lane = threadIdx.x & 31u;
+  const unsigned  lt   = (1u << lane) - 1u;
+
+  if(sc.numTris == 0)
+  {
+    // nothing to hit: every closest ray misses, every shadow ray is unoccluded
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+      const uint32_t slot = (MODE != MODE_SHADOW_RESOLVE && L.queue) ? L.queue[i] : i;
+      if(MODE == MODE_SHADOW_RESOLVE)
+      {
+        const float4 c = L.shC[i];
+        float4       r = L.rad[__float_as_uint(c.w)];
+        r.x += c.x; r.y += c.y; r.z += c.z;
+        L.rad[__float_as_uint(c.w)] = r;
+      }
+      else
+        L.hit[slot] = f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u));
+    }
+    return;
+  }
+
+  const float4* __restrict__ nodes = sc.nodes;
+  const float4* __restrict__ tris  = sc.tris;
+
+  // per-lane ray + traversal state (lives across refills)
+  bool     haveRay = false;
+  uint32_t slot = 0, seed = 0;
+  float3   o = f3(0.f), d = f3(0.f), id = f3(0.f);
+  float    tmax = 0.f, bestT = 0.f, bestU = 0.f, bestV = 0.f;
+  uint32_t bestTri = ~0u;
+  uint32_t node = kDone, leaf = 0;
+  int      sp = 0;
+  bool     exhausted = false;  // warp uniform: the queue has been handed out completely
+  uint32_t nNodes = 0, nTris = 0;
+
+  auto push = [&](uint32_t v) {
+    if(sp < kStackShared)
+      sstack[sp * kTraceBlock] = v;
+    else
+      lstack[min(sp - kStackShared, kStackLocal - 1)] = v;
+    sp++;
+  };
+  auto pop = [&]() -> uint32_t {
+    if(sp == 0)
+      return kDone;
+    --sp;
+    return sp < kStackShared ? sstack[sp * kTraceBlock] : lstack[min(sp - kStackShared, kStackLocal - 1)];
+  };
+
+  for(;;)
+  {
+    __syncwarp();
+    // ---- refill idle lanes ---------------------------------------------------------------
+    const unsigned idle = __ballot_sync(kFull, !haveRay);
+    if(idle && !exhausted)
+    {
+      const uint32_t want = (uint32_t)__popc(idle);
+      uint32_t       base = 0;
+      if(lane == 0)
+        base = atomicAdd(L.cursor, want);
+      base = __shfl_sync(kFull, base, 0);
+      if(!haveRay)
+      {
+        const uint32_t i = base + (uint32_t)__popc(idle & lt);
+        if(i < n)
+        {
+          slot = (MODE != MODE_SHADOW_RESOLVE && L.queue) ? L.queue[i] : i;
+          const float4 ro = L.rayO[slot], rd = L.rayD[slot];
+          o = f3(ro); d = f3(rd);
+          tmax = ro.w; seed = __float_as_uint(rd.w);
+          id      = f3(safeInv(d.x), safeInv(d.y), safeInv(d.z));
+          bestT   = tmax; bestU = 0.f; bestV = 0.f; bestTri = ~0u;
+          node    = 0; leaf = 0; sp = 0;
+          haveRay = true;
+        }
+      }
+      exhausted = (base + want >= n);
+    }
+    if(!__any_sync(kFull, haveRay))
+      break;
+
+    if(haveRay)
+    {
+      // single "if-if" loop: every iteration each lane does either one node step or one leaf
+      while(node != kDone)
+      {
+        if(node < kDone)
+        {
+          const float4 n0 = __ldg(&nodes[4ull * node + 0]);
+          const float4 n1 = __ldg(&nodes[4ull * node + 1]);
+          const float4 n2 = __ldg(&nodes[4ull * node + 2]);
+          const float4 n3 = __ldg(&nodes[4ull * node + 3]);
+          if(COUNT) nNodes++;
+          const float a0x = (n0.x - o.x) * id.x, b0x = (n0.y - o.x) * id.x;
+          const float a0y = (n0.z - o.y) * id.y, b0y = (n0.w - o.y) * id.y;
+          const float a0z = (n2.x - o.z) * id.z, b0z = (n2.y - o.z) * id.z;
+          const float a1x = (n1.x - o.x) * id.x, b1x = (n1.y - o.x) * id.x;
+          const float a1y = (n1.z - o.y) * id.y, b1y = (n1.w - o.y) * id.y;
+          const float a1z = (n2.z - o.z) * id.z, b1z = (n2.w - o.z) * id.z;
+          const float tn0 = fmaxf(fmaxf(fminf(a0x, b0x), fminf(a0y, b0y)), fmaxf(fminf(a0z, b0z), 0.0f));
+          const float tf0 = fminf(fminf(fmaxf(a0x, b0x), fmaxf(a0y, b0y)), fminf(fmaxf(a0z, b0z), bestT));
+          const float tn1 = fmaxf(fmaxf(fminf(a1x, b1x), fminf(a1y, b1y)), fmaxf(fminf(a1z, b1z), 0.0f));
+          const float tf1 = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fminf(fmaxf(a1z, b1z), bestT));
+          const bool  h0  = tn0 <= tf0 * 1.0002f;
+          const bool  h1  = tn1 <= tf1 * 1.0002f;
+          uint32_t    c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+          if(h0 && h1)
+          {
+            if(tn1 < tn0)
+            {
+              const uint32_t t = c0; c0 = c1; c1 = t;
+            }
+            push(c1);
+            node = c0;
+          }
+          else if(h0)
+            node = c0;
+          else if(h1)
+            node = c1;
+          else
+            node = pop();
+        }
+        else
+        {
+          const uint32_t first = node & kLeafMask;
+          const uint32_t cnt   = ((node >> kLeafCntSh) & 7u) + 1u;
+          node = pop();
+          for(uint32_t k = 0; k < cnt; k++)
+          {
+            const float4 q0 = __ldg(&tris[3ull * (first + k) + 0]);
+            const float4 q1 = __ldg(&tris[3ull * (first + k) + 1]);
+            const float4 q2 = __ldg(&tris[3ull * (first + k) + 2]);
+            if(COUNT) nTris++;
+            const uint32_t flags = __float_as_uint(q0.w);
+            const uint32_t triId = __float_as_uint(q1.w);
+            const float3 v0  = f3(q0);
+            const float3 e1  = f3(q1) - v0;
+            const float3 e2  = f3(q2) - v0;
+            const float3 p   = cross(d, e2);
+            const float  det = dot(e1, p);
+            if(!(flags & TRI_CULL_DISABLE))
+            {
+              const bool front = (flags & TRI_FLIP_FACING) ? (det < 0.0f) : (det > 0.0f);
+              if(!front)
+                continue;
+            }
+            if(det == 0.0f || !(det == det))
+              continue;
+            const float  inv = 1.0f / det;
+            const float3 tv  = o - v0;
+            const float  u   = dot(tv, p) * inv;
+            if(!(u >= 0.0f && u <= 1.0f))
+              continue;
+            const float3 q = cross(tv, e1);
+            const float  v = dot(d, q) * inv;
+            if(!(v >= 0.0f && (u + v) <= 1.0f))
+              continue;
+            const float t = dot(e2, q) * inv;
+            if(!(t > 0.0f && t < tmax))
+              continue;
+            if(!(t < bestT || (t == bestT && triId < bestTri)))
+              continue;
+            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, u, v, seed))
+              continue;
+            bestT = t; bestU = u; bestV = v; bestTri = triId;
+            if(MODE != MODE_CLOSEST)
+            {
+              node = kDone;  // TerminateOnFirstHit
+              sp   = 0;
+              break;
+            }
+          }
+        }
+        if(!exhausted && __popc(__activemask()) < kRefetchThreshold)
+          break;
+      }
+
+      if(node == kDone && leaf == 0)
+      {
+        if(MODE == MODE_CLOSEST)
+          L.hit[slot] = (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(bestT, bestU, bestV, __uint_as_float(bestTri));
+        else if(MODE == MODE_ANY_PROBE)
+          L.hit[slot] = (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(0.f, 0.f, 0.f, __uint_as_float(0u));
+        else if(bestTri == ~0u)
+        {
+          // unoccluded: radiance += contribution (one shadow ray per path per bounce: no race)
+          const float4   c    = L.shC[slot];
+          const uint32_t path = __float_as_uint(c.w);
+          float4         rad  = L.rad[path];
+          rad.x += c.x; rad.y += c.y; rad.z += c.z;
+          L.rad[path] = rad;
+        }
+        haveRay = false;
+      }
+    }
+  }
+
+  if(COUNT && L.stats)
+  {
+    atomicAdd(&L.stats->nodesVisited, (unsigned long long)nNodes);
+    atomicAdd(&L.stats->trisTested, (unsigned long long)nTris);
+    if(MODE == MODE_SHADOW_RESOLVE)
+    {
+      atomicAdd(&L.stats->shadowNodes, (unsigned long long)nNodes);
+      atomicAdd(&L.stats->shadowTris, (unsigned long long)nTris);
+    }
+  }
+}
+
+
+
 // ==========================================================================================================
 // Warp-cooperative variant ("leaf queue").  Lanes own rays for the box tests, but triangle tests are handed to
 // a warp-shared queue in shared memory and executed 32 at a time by whichever lanes are free, so neither phase
@@ -644,6 +863,19 @@ static void launchTraceCoop(cudaStream_t s, const SceneView& scene, const TraceL
   traceKernelCoop<MODE, COUNT><<<grid, kTraceBlock, 0, s>>>(scene, L);
 }
 
+template <int MODE, bool COUNT>
+static void launchTraceIfIf(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, int numSMs)
+{
+  static int grid = 0;
+  if(!grid)
+  {
+    int perSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernelIfIf<MODE, COUNT>, kTraceBlock, 0);
+    grid = numSMs * (perSM < 1 ? 1 : perSM);
+  }
+  traceKernelIfIf<MODE, COUNT><<<grid, kTraceBlock, 0, s>>>(scene, L);
+}
+
 template <int MODE, bool COUNT, int VARIANT>
 static void launchTraceV(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, int numSMs)
 {
@@ -668,6 +900,7 @@ static void launchTrace(cudaStream_t s, const SceneView& scene, const TraceLaunc
   switch(variant)
   {
     case 100: launchTraceCoop<MODE, COUNT>(s, scene, L, numSMs); break;
+    case 200: launchTraceIfIf<MODE, COUNT>(s, scene, L, numSMs); break;
     case 1: launchTraceV<MODE, COUNT, 1>(s, scene, L, numSMs); break;
     case 4: launchTraceV<MODE, COUNT, 4>(s, scene, L, numSMs); break;
     case 8: launchTraceV<MODE, COUNT, 8>(s, scene, L, numSMs); break;
