@@ -9,6 +9,7 @@
 #include <string>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include "vkrt_device.cuh"
 #include "vkrt_internal.h"
@@ -117,7 +118,7 @@ static void freeScene(vkrt_ctx* c)
   cudaFree(c->dMat); cudaFree(c->dLights); cudaFree(c->dTexDescs);
   for(auto p : c->dTexData) cudaFree(p);
   c->dTexData.clear();
-  cudaFree(c->bvh.nodes); cudaFree(c->bvh.tris); cudaFree(c->bvh.triInfo); cudaFree(c->bvh.triShade);
+  cudaFree(c->bvh.nodes); cudaFree(c->bvh.triInfo); cudaFree(c->bvh.triShade);
   c->dVerts = nullptr; c->dIdx = nullptr; c->dGeo = nullptr; c->dInst = nullptr; c->dInstTriOffset = nullptr;
   c->dMat = nullptr; c->dLights = nullptr; c->dTexDescs = nullptr;
   c->bvh = BvhResult{};
@@ -468,10 +469,9 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
       return fail(ctx, VKRT_ERR_INVALID, "scene_commit: host SAH build failed");
     for(uint32_t i = 0; i < nt; i++)
       std::memcpy(&sorted[12ull * i], &htris[12ull * order[i]], 48);
-    cudaFree(ctx->bvh.nodes);
-    ctx->bvh.nodes = nullptr;
-    ctx->bvh.numNodes = (uint32_t)(hnodes.size() / 16);
-    CTX_CHECK(cudaMalloc(&ctx->bvh.nodes, hnodes.size() * sizeof(float)));
+    if(hnodes.size() / 16 > ctx->bvh.numNodes)
+      return fail(ctx, VKRT_ERR_INVALID, "scene_commit: host SAH produced more nodes than the arena holds");
+    ctx->bvh.numNodes = (uint32_t)(hnodes.size() / 16);  // <= n - 1: fits the arena of the GPU build
     CTX_CHECK(cudaMemcpy(ctx->bvh.nodes, hnodes.data(), hnodes.size() * sizeof(float), cudaMemcpyHostToDevice));
     CTX_CHECK(cudaMemcpy(ctx->bvh.tris, sorted.data(), sorted.size() * sizeof(float), cudaMemcpyHostToDevice));
     ctx->bvh.maxDepth = depth;
@@ -488,6 +488,27 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
   ctx->stats.num_instances  = (uint32_t)inst.size();
   ctx->stats.has_non_opaque = nonOpaque ? 1u : 0u;
 
+  // Keep the BVH resident in L2: mark its arena persisting and everything else streaming for this stream's kernels
+  // (the wavefront state streams hundreds of MB per bounce through the same L2).
+  {
+    const char* e = getenv("VKRT_L2_PERSIST");
+    int maxWin = 0, maxPersist = 0;
+    cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device);
+    cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device);
+    if((!e || atoi(e) != 0) && maxWin > 0 && maxPersist > 0 && ctx->bvh.arenaBytes > 0)
+    {
+      const size_t want = std::min<size_t>(ctx->bvh.arenaBytes, (size_t)maxPersist);
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+      cudaStreamAttrValue attr{};
+      attr.accessPolicyWindow.base_ptr  = ctx->bvh.nodes;
+      attr.accessPolicyWindow.num_bytes = std::min<size_t>(ctx->bvh.arenaBytes, (size_t)maxWin);
+      attr.accessPolicyWindow.hitRatio  = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
+      attr.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+      cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      cudaGetLastError();
+    }
+  }
   SceneView& v   = ctx->view;
   v.nodes        = ctx->bvh.nodes;
   v.tris         = ctx->bvh.tris;

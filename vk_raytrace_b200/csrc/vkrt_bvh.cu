@@ -354,8 +354,10 @@ bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* d
   const int B = 256;
   uint32_t  numNodes = numTris > 1 ? numTris - 1 : 1;
 
-  CK(cudaMalloc(&out.nodes, sizeof(float4) * 4ull * numNodes));
-  CK(cudaMalloc(&out.tris, sizeof(float4) * 3ull * (numTris ? numTris : 1)));
+  // nodes and triangles share one allocation so that a single L2 access-policy window can cover the BVH
+  CK(cudaMalloc(&out.nodes, sizeof(float4) * (4ull * numNodes + 3ull * (numTris ? numTris : 1))));
+  out.tris       = out.nodes + 4ull * numNodes;
+  out.arenaBytes = sizeof(float4) * (4ull * numNodes + 3ull * (numTris ? numTris : 1));
   CK(cudaMalloc(&out.triInfo, sizeof(uint2) * (numTris ? numTris : 1)));
   CK(cudaMalloc(&out.triShade, sizeof(uint4) * 7ull * (numTris ? numTris : 1)));
   out.numNodes = numNodes;
@@ -414,7 +416,7 @@ fail:
   cudaFree(wtri); cudaFree(bounds); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB); cudaFree(cubTemp);
   cudaFree(children); cudaFree(ranges); cudaFree(parentInner); cudaFree(parentLeaf); cudaFree(flags); cudaFree(nodeDepth);
   cudaFree(maxDepthDev); cudaFree(leafBox); cudaFree(nodeBox); cudaFree(nodeCost); cudaFree(collapsed);
-  cudaFree(out.nodes); cudaFree(out.tris); cudaFree(out.triInfo); cudaFree(out.triShade);
+  cudaFree(out.nodes); cudaFree(out.triInfo); cudaFree(out.triShade);
   out = BvhResult{};
   return false;
 }

@@ -15,7 +15,8 @@ struct TraceStats;
 struct BvhResult
 {
   float4*  nodes    = nullptr;
-  float4*  tris     = nullptr;
+  float4*  tris     = nullptr;  // inside the nodes allocation
+  size_t   arenaBytes = 0;
   uint2*   triInfo  = nullptr;
   uint4*   triShade = nullptr;  // 7 x uint4 per flattened triangle
   uint32_t numNodes = 0;

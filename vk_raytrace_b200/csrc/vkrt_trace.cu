@@ -28,10 +28,19 @@
 
 namespace vkrt {
 
-constexpr int      kTraceBlock       = 128;
-constexpr int      kStackShared      = 32;  // entries per thread in shared memory
-constexpr int      kStackLocal       = 96;  // overflow entries in local memory
-constexpr int      kRefetchThreshold = 24;  // refill the warp when fewer lanes than this are traversing
+#ifndef VKRT_STACK_SHARED
+#define VKRT_STACK_SHARED 32
+#endif
+#ifndef VKRT_REFETCH
+#define VKRT_REFETCH 24
+#endif
+#ifndef VKRT_TRACE_BLOCK
+#define VKRT_TRACE_BLOCK 128
+#endif
+constexpr int      kTraceBlock       = VKRT_TRACE_BLOCK;
+constexpr int      kStackShared      = VKRT_STACK_SHARED;  // entries per thread in shared memory
+constexpr int      kStackLocal       = 128 - VKRT_STACK_SHARED;  // overflow entries in local memory
+constexpr int      kRefetchThreshold = VKRT_REFETCH;  // refill the warp when fewer lanes than this are traversing
 constexpr uint32_t kDone             = 0x7fffffffu;  // traversal finished (never a node index)
 constexpr unsigned kFull             = 0xffffffffu;
 
@@ -60,6 +69,19 @@ __device__ __noinline__ bool alphaTestPasses(const SceneView& sc, uint32_t triId
   }
   float opacity = (mat.alphaMode == VKRT_ALPHA_MASK) ? (baseColorAlpha > mat.alphaCutoff ? 1.0f : 0.0f) : baseColorAlpha;
   return !(alphaDraw(raySeed, triId) > opacity);
+}
+
+// One 64-byte node as two 256-bit loads (sm_100 LDG.E.256): the traversal is bound by L1 wavefronts of per-lane
+// gathers, and two 32-byte requests per node cost half the tag/wavefront work of four 16-byte ones.
+VKRT_D void loadNode256(const float4* __restrict__ nodes, uint32_t node, float4& n0, float4& n1, float4& n2, float4& n3)
+{
+  const float4* p = nodes + 4ull * node;
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(n0.x), "=f"(n0.y), "=f"(n0.z), "=f"(n0.w), "=f"(n1.x), "=f"(n1.y), "=f"(n1.z), "=f"(n1.w)
+      : "l"(p));
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=f"(n2.x), "=f"(n2.y), "=f"(n2.z), "=f"(n2.w), "=f"(n3.x), "=f"(n3.y), "=f"(n3.z), "=f"(n3.w)
+      : "l"(p + 2));
 }
 
 VKRT_D float safeInv(float x) { return 1.0f / (fabsf(x) < 1e-20f ? copysignf(1e-20f, x) : x); }
@@ -160,10 +182,8 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernel(const __grid_const
         // ---- inner nodes, until every lane of the warp has parked a leaf ---------------------
         while(node < kDone)  // inner index (leaf codes have bit 31 set, kDone is larger than any index)
         {
-          const float4 n0 = __ldg(&nodes[4ull * node + 0]);
-          const float4 n1 = __ldg(&nodes[4ull * node + 1]);
-          const float4 n2 = __ldg(&nodes[4ull * node + 2]);
-          const float4 n3 = __ldg(&nodes[4ull * node + 3]);
+          float4 n0, n1, n2, n3;
+          loadNode256(nodes, node, n0, n1, n2, n3);
           if(COUNT) nNodes++;
           const float a0x = (n0.x - o.x) * id.x, b0x = (n0.y - o.x) * id.x;
           const float a0y = (n0.z - o.y) * id.y, b0y = (n0.w - o.y) * id.y;
@@ -416,10 +436,8 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernelIfIf(const __grid_c
       {
         if(node < kDone)
         {
-          const float4 n0 = __ldg(&nodes[4ull * node + 0]);
-          const float4 n1 = __ldg(&nodes[4ull * node + 1]);
-          const float4 n2 = __ldg(&nodes[4ull * node + 2]);
-          const float4 n3 = __ldg(&nodes[4ull * node + 3]);
+          float4 n0, n1, n2, n3;
+          loadNode256(nodes, node, n0, n1, n2, n3);
           if(COUNT) nNodes++;
           const float a0x = (n0.x - o.x) * id.x, b0x = (n0.y - o.x) * id.x;
           const float a0y = (n0.z - o.y) * id.y, b0y = (n0.w - o.y) * id.y;
@@ -669,10 +687,8 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernelCoop(const __grid_c
       if(work)
       {
         const float  bestT = __uint_as_float((uint32_t)(myKey >> 32));
-        const float4 n0 = __ldg(&nodes[4ull * node + 0]);
-        const float4 n1 = __ldg(&nodes[4ull * node + 1]);
-        const float4 n2 = __ldg(&nodes[4ull * node + 2]);
-        const float4 n3 = __ldg(&nodes[4ull * node + 3]);
+        float4 n0, n1, n2, n3;
+        loadNode256(nodes, node, n0, n1, n2, n3);
         if(COUNT) nNodes++;
         const float a0x = (n0.x - o.x) * id.x, b0x = (n0.y - o.x) * id.x;
         const float a0y = (n0.z - o.y) * id.y, b0y = (n0.w - o.y) * id.y;

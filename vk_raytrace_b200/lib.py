@@ -14,7 +14,8 @@ class LibraryMissing(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libvkrt_b200.so")
+    # VKRT_LIB_PATH: A/B builds during bring-up; the default is the in-tree library
+    return os.environ.get("VKRT_LIB_PATH") or os.path.join(_HERE, "libvkrt_b200.so")
 
 
 # every symbol include/vkrt_b200.h declares
