@@ -262,22 +262,31 @@ def main():
             traffic = json.load(open(prof)).get("traceClosestKernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    n_launch = max(1, (args.steps + max(1, 1) - 1))  # informational only
-    roofline = {"kernel": "traceClosestKernel", "bound": "hbm", "achieved": ach_closest, "peak": peak, "unit": "GB/s", "frac": ach_closest / peak,
+    # the resource that actually binds the traversal: the L1 data pipe serves one cache-line wavefront per clock per SM and a
+    # node step of a lane is two of them (64-B node fetched as two 32-B halves), see profiles/README.md
+    sm_clk = (sampler.summary()["sm_mhz"] or 1965.0) * 1e6
+    steps_per_s = c_nodes / max(kernel_ms["trace_closest"], 1e-9) * 1e3
+    l1_peak = 148 * sm_clk * 0.5
+    roofline = {"kernel": "traceKernel<CLOSEST>", "bound": "hbm", "achieved": ach_closest, "peak": peak, "unit": "GB/s", "frac": ach_closest / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "per_ray": {"nodes": c_nodes / max(1, sc.closest_rays), "tris": c_tris / max(1, sc.closest_rays),
                             "bytes": bytes_closest / max(1, sc.closest_rays)},
                 "shadow_kernel": {"achieved": ach_shadow, "frac": ach_shadow / peak,
                                   "nodes_per_ray": sc.shadow_nodes_visited / max(1, sc.shadow_rays),
                                   "tris_per_ray": sc.shadow_tris_tested / max(1, sc.shadow_rays)},
-                "note": "algorithmic bytes / CUDA-event kernel time; the BVH is L2-resident, so DRAM traffic is far below algorithmic bytes"}
+                "l1_gather": {"achieved_gsteps_per_s": steps_per_s / 1e9, "peak_gsteps_per_s": l1_peak / 1e9, "frac": steps_per_s / l1_peak,
+                              "what": "BVH node steps/s vs 148 SMs x SM clock x 0.5 (one L1 wavefront per clock per SM, two per 64-B node)"},
+                "note": "algorithmic bytes (SURVEY 8d) / summed CUDA-event kernel time.  For L2-resident scenes (this one: 30 MB BVH) the "
+                        "algorithmic rate exceeds the HBM peak because node traffic is served by L1/L2; DRAM traffic (`traffic`, ncu) is only "
+                        "the ray/hit streams.  The kernel is bound by L1 gather wavefronts (l1_gather), not by HBM; the HBM-resident case is "
+                        "the instanced_10m workload."}
 
     # ---- e2e: host buffers in, host image out, every step through the C ABI (rank-local; N=1 only)
     e2e = None
     if not args.no_e2e and not use_dist:
         cam = scene.camera
         tm = S.default_tonemapper()
-        out8 = np.empty((H, W, 4), dtype=np.uint8)
+        out8 = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()   # pinned host frame buffer
         opts_e = S.RenderOpts()
         k = max(4, min(args.steps, 16))
         for f in range(2):
@@ -297,7 +306,8 @@ def main():
         se = ctx.stats()
         e2e = {"value": (se.closest_rays + se.shadow_rays) / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 140 + 48,
                "d2h_bytes_per_step": W * H * 4, "steps": k, "ms_per_step": dt / k * 1e3,
-               "what": "per step: vkrt_set_camera(host SceneCamera) + vkrt_render(1 frame) + vkrt_tonemap -> host RGBA8"}
+               "what": "per step: vkrt_set_camera(host SceneCamera) + vkrt_render(1 frame) + vkrt_tonemap -> pinned host RGBA8 "
+                       "(interactive use: one frame per call, so no multi-frame batching)"}
     elif use_dist:
         # per step host traffic is the same tiny parameter upload; the image comes back once after the reduce
         t0 = time.time()

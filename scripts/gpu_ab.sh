@@ -5,5 +5,4 @@ import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); k=d['kernel_ms']
 print('$1  Mrays/s=%.0f wall=%.1f closest=%.1f shadow=%.1f shade=%.1f' % (d['value'],d['wall_ms'],k['trace_closest'],k['trace_shadow'],k['shade']))"; }
 run base
-VKRT_L2_PERSIST=0 run nopersist
-for n in S16 S8 R16 R30; do VKRT_LIB_PATH=$PWD/vk_raytrace_b200/libvkrt_var_$n.so run $n; done
+for n in A B C D E; do VKRT_LIB_PATH=$PWD/vk_raytrace_b200/libvkrt_var_$n.so run $n; done

@@ -19,8 +19,12 @@
 
 namespace vkrt {
 
-constexpr int kShadeBlock     = 320;
-constexpr int kShadeMinBlocks = 2;  // <= 96 registers: 640 threads per SM; large CTAs so that the phase barriers keep many warps in step
+#ifndef VKRT_SHADE_BLOCK
+#define VKRT_SHADE_BLOCK 384
+#define VKRT_SHADE_MINBLOCKS 2
+#endif
+constexpr int kShadeBlock     = VKRT_SHADE_BLOCK;
+constexpr int kShadeMinBlocks = VKRT_SHADE_MINBLOCKS;  // <= 96 registers: 640 threads per SM; large CTAs so that the phase barriers keep many warps in step
 
 // ---- ray generation: pathtrace.comp:97 / pathtrace.rgen:72 + pathtrace.glsl:348-376 -------------------
 __global__ void __launch_bounds__(256) raygenKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
