@@ -1,0 +1,162 @@
+"""CPU tests of the glTF / image ingest path (vk_raytrace_b200/host/): the host half of Scene::load (src/scene.cpp:56-118)
+and HdrSampling::loadEnvironment's decoder (src/hdr_sampling.cpp:64), restated without tinygltf / stb_image."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import small_sponza
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "vk_raytrace_b200", "host")
+
+
+@pytest.fixture(scope="module")
+def selftest(built):
+    exe = os.path.join(HOST, "vkrt_host_selftest")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    return exe
+
+
+def decode_png(selftest, path, tmp_path):
+    raw = str(tmp_path / "out.raw")
+    out = subprocess.run([selftest, "png", path, raw], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    w, h = map(int, out.stdout.split())
+    return np.fromfile(raw, dtype=np.uint8).reshape(h, w, 4)
+
+
+def test_png_decoder_matches_pillow(selftest, tmp_path):
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    rgba = rng.integers(0, 256, (37, 53, 4), dtype=np.uint8)
+    cases = {
+        "rgba": Image.fromarray(rgba, "RGBA"), "rgb": Image.fromarray(rgba[..., :3].copy(), "RGB"), "gray": Image.fromarray(rgba[..., 0].copy(), "L"),
+        "la": Image.fromarray(rgba[..., [0, 3]].copy(), "LA"), "pal": Image.fromarray(rgba[..., :3].copy(), "RGB").quantize(32),
+        "big": Image.fromarray(np.tile(rgba, (8, 6, 1)), "RGBA"),
+    }
+    for name, im in cases.items():
+        for opts in ({}, {"optimize": True}, {"compress_level": 0}):
+            p = str(tmp_path / f"{name}.png")
+            im.save(p, **opts)
+            got = decode_png(selftest, p, tmp_path)
+            want = np.asarray(Image.open(p).convert("RGBA"))
+            assert np.array_equal(got, want), (name, opts)
+    # 16-bit: the decoder keeps the high byte (what stb_image's 8-bit path does)
+    g16 = (rng.integers(0, 65536, (9, 11), dtype=np.uint16))
+    p = str(tmp_path / "g16.png")
+    Image.fromarray(g16, "I;16").save(p)
+    got = decode_png(selftest, p, tmp_path)
+    assert np.array_equal(got[..., 0], (g16 >> 8).astype(np.uint8)) and np.all(got[..., 3] == 255)
+    # our own writer (used by the glTF exporter)
+    from vk_raytrace_b200.gltf_export import write_png
+    p = str(tmp_path / "own.png")
+    write_png(p, rgba)
+    assert np.array_equal(decode_png(selftest, p, tmp_path), rgba)
+
+
+def test_png_adam7_interlaced(selftest, tmp_path):
+    """Hand-assembled Adam7 PNG (Pillow cannot write interlaced files)."""
+    import zlib
+    rng = np.random.default_rng(5)
+    h, w = 13, 10
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    raw = b""
+    for x0, y0, dx, dy in [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)]:
+        sub = img[y0::dy, x0::dx]
+        if sub.size:
+            raw += b"".join(b"\x00" + sub[y].tobytes() for y in range(sub.shape[0]))
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+    p = str(tmp_path / "a7.png")
+    open(p, "wb").write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 1)) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b""))
+    got = decode_png(selftest, p, tmp_path)
+    assert np.array_equal(got[..., :3], img) and np.all(got[..., 3] == 255)
+
+
+def test_hdr_and_pfm_readers(selftest, tmp_path):
+    from vk_raytrace_b200 import scenes
+    from vk_raytrace_b200.gltf_export import write_pfm
+    env = scenes.sky_environment(64, 32, 9)
+    p = str(tmp_path / "e.pfm")
+    write_pfm(p, env)
+    raw = str(tmp_path / "e.raw")
+    out = subprocess.run([selftest, "hdr", p, raw], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["64", "32"]
+    got = np.fromfile(raw, dtype=np.float32).reshape(32, 64, 4)
+    assert np.array_equal(got[..., :3], env[..., :3]) and np.all(got[..., 3] == 1.0)
+    # Radiance RGBE, flat and run-length encoded scanlines; decode = mantissa * 2^(e-136) (stb_image's hdr_convert)
+    rgb = env[..., :3].astype(np.float64)
+    m = rgb.max(axis=2)
+    e = np.where(m > 1e-32, np.ceil(np.log2(np.maximum(m, 1e-38)) + 1e-12), -128).astype(int)
+    rgbe = np.zeros((32, 64, 4), dtype=np.uint8)
+    scale = np.where(m > 1e-32, 256.0 / (2.0 ** e), 0.0)
+    rgbe[..., :3] = np.clip(np.floor(rgb * scale[..., None]), 0, 255).astype(np.uint8)
+    rgbe[..., 3] = np.where(m > 1e-32, e + 128, 0).astype(np.uint8)
+    want = np.where(rgbe[..., 3:4] > 0, rgbe[..., :3].astype(np.float32) * np.ldexp(1.0, rgbe[..., 3:4].astype(int) - 136).astype(np.float32), 0).astype(np.float32)
+    for mode in ("flat", "rle"):
+        body = b""
+        for y in range(32):
+            if mode == "flat":
+                body += rgbe[y].tobytes()
+            else:
+                body += bytes([2, 2, 0, 64])
+                for c in range(4):
+                    row = rgbe[y, :, c]
+                    x = 0
+                    while x < 64:
+                        n = min(64 - x, 100)
+                        if x % 2 == 0 and np.all(row[x:x + n] == row[x]) and n > 2:
+                            body += bytes([128 + n, row[x]])
+                        else:
+                            body += bytes([n]) + row[x:x + n].tobytes()
+                        x += n
+        p = str(tmp_path / f"{mode}.hdr")
+        open(p, "wb").write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 32 +X 64\n" + body)
+        out = subprocess.run([selftest, "hdr", p, raw], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        got = np.fromfile(raw, dtype=np.float32).reshape(32, 64, 4)
+        assert np.array_equal(got[..., :3], want), mode
+
+
+def test_gltf_import_matches_exported_scene(selftest, tmp_path):
+    """Export the Sponza stand-in as glTF (.gltf + .bin + PNG) and read it back through the C++ importer."""
+    from vk_raytrace_b200.gltf_export import export_gltf
+    sc = small_sponza()
+    gltf, env = export_gltf(sc, str(tmp_path), "s")
+    out = subprocess.run([selftest, "gltf", gltf], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    kv = lines[0].split()
+    summary = dict(zip(kv[0::2][:7], kv[1::2][:7]))
+    assert int(summary["primMeshes"]) == len(sc.meshes) and int(summary["nodes"]) == len(sc.nodes)
+    assert int(summary["triangles"]) == sc.num_triangles() and int(summary["materials"]) == len(sc.materials)
+    assert int(summary["textures"]) == len(sc.textures) and int(summary["lights"]) == len(sc.lights) and summary["camera"] == "1"
+    sums = dict(zip(lines[1].split()[0::2], map(float, lines[1].split()[1::2])))
+    want_pos = sum(float(m.positions.astype(np.float64).sum()) for m in sc.meshes)
+    want_idx = sum(float(m.indices.astype(np.float64).sum()) for m in sc.meshes)
+    M = sc.materials
+    want_mat = float((M["pbrRoughnessFactor"].astype(np.float64) + M["pbrMetallicFactor"] + M["pbrBaseColorFactor"][:, 0] + M["alphaMode"] + M["doubleSided"]
+                      + M["clearcoatFactor"] + M["transmissionFactor"] + M["ior"] + M["anisotropy"] + M["sheen"].astype(np.float64)).sum())
+    assert abs(sums["sumPos"] - want_pos) < 1e-3 * max(1, abs(want_pos)) and sums["sumIdx"] == want_idx
+    assert abs(sums["sumMat"] - want_mat) < 1e-6 * want_mat
+    spot = [l for l in lines if l.startswith("light type 2")][0].split()
+    assert np.allclose([float(v) for v in spot[8:11]], sc.lights["direction"][1], atol=1e-6)
+    assert abs(float(spot[-2]) - float(sc.lights["innerConeCos"][1])) < 1e-6
+    # .glb container: same JSON + BIN in one file
+    import json
+    doc = json.load(open(gltf))
+    binb = open(os.path.join(str(tmp_path), "s.bin"), "rb").read()
+    del doc["buffers"][0]["uri"]
+    js = json.dumps(doc).encode()
+    js += b" " * (-len(js) % 4)
+    binb += b"\0" * (-len(binb) % 4)
+    glb = str(tmp_path / "s.glb")
+    open(glb, "wb").write(struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(js) + 8 + len(binb)) + struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(binb), 0x004E4942) + binb)
+    out2 = subprocess.run([selftest, "gltf", glb], capture_output=True, text=True)
+    assert out2.returncode == 0 and out2.stdout.splitlines()[1] == lines[1]
