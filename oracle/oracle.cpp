@@ -127,8 +127,92 @@ static vec3 dither(vec3 linear_color, vec3 noise, float quant)
   // mix(c0, c1, lessThan(discr, linear_color))
   return V3(discr.x < linear_color.x ? c1.x : c0.x, discr.y < linear_color.y ? c1.y : c0.y, discr.z < linear_color.z ? c1.z : c0.z);
 }
-// post.frag:98-147 with autoExposure == 0 (mip-pyramid exposure is SURVEY 8f-3)
-static vec4 postPixel(const Tonemapper& tm, const float* image, int W, int H, int x, int y)
+// ---- mip pyramid for auto-exposure: RenderOutput::genMipmap (src/render_output.cpp:188-193) = nvvk::cmdGenerateMipmaps,
+// i.e. vkCmdBlitImage(level k -> k+1, VK_FILTER_LINEAR) with extent max(1, size >> 1) per level.  A scaling blit samples the
+// source at u = (x + 0.5) * srcW / dstW with linear filtering and clamp-to-edge.
+struct MipChain
+{
+  std::vector<std::vector<float>> level;  // RGBA32F
+  std::vector<int>                w, h;
+};
+static MipChain buildMipChain(const float* image, int W, int H)
+{
+  MipChain m;
+  m.level.emplace_back(image, image + size_t(W) * H * 4);
+  m.w.push_back(W); m.h.push_back(H);
+  while(m.w.back() > 1 || m.h.back() > 1)
+  {
+    const int sw = m.w.back(), sh = m.h.back(), dw = std::max(1, sw >> 1), dh = std::max(1, sh >> 1);
+    const std::vector<float>& src = m.level.back();
+    std::vector<float> dst(size_t(dw) * dh * 4);
+    for(int y = 0; y < dh; y++)
+      for(int x = 0; x < dw; x++)
+      {
+        const float u = ((float)x + 0.5f) * ((float)sw / (float)dw) - 0.5f, v = ((float)y + 0.5f) * ((float)sh / (float)dh) - 0.5f;
+        const float x0f = std::floor(u), y0f = std::floor(v), ax = u - x0f, ay = v - y0f;
+        const int   x0 = std::min(sw - 1, std::max(0, (int)x0f)), x1 = std::min(sw - 1, std::max(0, (int)x0f + 1));
+        const int   y0 = std::min(sh - 1, std::max(0, (int)y0f)), y1 = std::min(sh - 1, std::max(0, (int)y0f + 1));
+        for(int c = 0; c < 4; c++)
+        {
+          const float c00 = src[(size_t(y0) * sw + x0) * 4 + c], c10 = src[(size_t(y0) * sw + x1) * 4 + c];
+          const float c01 = src[(size_t(y1) * sw + x0) * 4 + c], c11 = src[(size_t(y1) * sw + x1) * 4 + c];
+          const float top = c00 * (1.0f - ax) + c10 * ax, bot = c01 * (1.0f - ax) + c11 * ax;
+          dst[(size_t(y) * dw + x) * 4 + c] = top * (1.0f - ay) + bot * ay;
+        }
+      }
+    m.level.push_back(std::move(dst));
+    m.w.push_back(dw); m.h.push_back(dh);
+  }
+  return m;
+}
+// NEAREST fetch of mip `lod` at uv (the post sampler is a default VkSamplerCreateInfo: NEAREST filters, NEAREST mipmap mode,
+// maxLod = FLT_MAX, src/render_output.cpp:96-98); lod is clamped to the chain.
+static vec3 mipFetch(const MipChain& m, vec2 uv, int lod)
+{
+  lod = std::min(std::max(lod, 0), (int)m.level.size() - 1);
+  const int w = m.w[lod], h = m.h[lod];
+  const int x = std::min(w - 1, std::max(0, (int)std::floor(uv.x * (float)w))), y = std::min(h - 1, std::max(0, (int)std::floor(uv.y * (float)h)));
+  const float* p = &m.level[lod][(size_t(y) * w + x) * 4];
+  return V3(p[0], p[1], p[2]);
+}
+static float postLuminance(vec3 c) { return dot(c, V3(0.2126f, 0.7152f, 0.0722f)); }  // post.frag:58-61
+// post.frag:57 RGB2XYZ is built column-major from the row-major literature matrix, so XYZ.y uses the second *column*
+static float xyzY(vec3 rgb) { return (0.3575761f * rgb.x + 0.7151522f * rgb.y) + 0.1191920f * rgb.z; }
+// post.frag:64-70
+static vec3 toneExposure(const Tonemapper& tm, vec3 RGB, float logAvgLum)
+{
+  const float XYZy = xyzY(RGB);
+  const float Y    = (tm.key / logAvgLum) * XYZy;
+  const float Yd   = (Y * (1.0f + Y / (tm.Ywhite * tm.Ywhite))) / (1.0f + Y);
+  return RGB / XYZy * Yd;
+}
+// post.frag:72-95
+static vec3 toneLocalExposure(const Tonemapper& tm, const MipChain& m, vec2 uv, vec3 RGB, float logAvgLum)
+{
+  const float XYZy = xyzY(RGB);
+  const float Y    = (tm.key / logAvgLum) * XYZy;
+  float       La   = 0.f;
+  const float factor = tm.key / logAvgLum;
+  const float epsilon = 0.05f, phi = 2.0f;
+  const float scale[7] = {1, 2, 4, 8, 16, 32, 64};
+  for(int i = 0; i < 7; ++i)
+  {
+    const float v1 = postLuminance(mipFetch(m, uv, i)) * factor;
+    const float v2 = postLuminance(mipFetch(m, uv, i + 1)) * factor;
+    if(std::fabs(v1 - v2) / ((tm.key * std::pow(2.0f, phi) / (scale[i] * scale[i])) + v1) > epsilon)
+    {
+      La = v1;
+      break;
+    }
+    else
+      La = v2;
+  }
+  const float Yd = Y / (1.0f + La);
+  return RGB / XYZy * Yd;
+}
+
+// post.frag:98-147
+static vec4 postPixel(const Tonemapper& tm, const float* image, int W, int H, int x, int y, const MipChain* mips)
 {
   vec2 uvCoords = V2(((float)x + 0.5f) / (float)W, ((float)y + 0.5f) / (float)H);
   // NEAREST sampling at uvCoords * zoom (src/render_output.cpp:96-98: default sampler)
@@ -136,6 +220,15 @@ static vec4 postPixel(const Tonemapper& tm, const float* image, int W, int H, in
   int sy = std::min(H - 1, std::max(0, (int)std::floor(uvCoords.y * tm.zoom * (float)H)));
   const float* p = image + (size_t(sy) * W + sx) * 4;
   vec3 hdr = V3(p[0], p[1], p[2]);
+  if(((tm.autoExposure >> 0) & 1) == 1 && mips)
+  {
+    const vec3  avg     = mipFetch(*mips, V2(0.5f, 0.5f), 20);  // textureLod(inImage, vec2(0.5), 20): the 1x1 top level
+    const float avgLum2 = postLuminance(avg);
+    if(((tm.autoExposure >> 1) & 1) == 1)
+      hdr = toneLocalExposure(tm, *mips, V2(uvCoords.x * tm.zoom, uvCoords.y * tm.zoom), hdr, avgLum2);
+    else
+      hdr = toneExposure(tm, hdr, avgLum2);
+  }
   vec3 color = toneMapUncharted(hdr * tm.avgLum);
   if(tm.dither > 0)
   {
@@ -377,10 +470,13 @@ int oracle_render(OracleCtx* c, const RtxState* state, int32_t num_frames, int32
 int oracle_tonemap(OracleCtx* c, const Tonemapper* tm, float* out_rgba32f, uint8_t* out_rgba8)
 {
   const int W = c->width, H = c->height;
+  MipChain  mips;
+  if(tm->autoExposure & 1)
+    mips = buildMipChain(c->image.data(), W, H);
   for(int y = 0; y < H; y++)
     for(int x = 0; x < W; x++)
     {
-      vec4   v = postPixel(*tm, c->image.data(), W, H, x, y);
+      vec4   v = postPixel(*tm, c->image.data(), W, H, x, y, (tm->autoExposure & 1) ? &mips : nullptr);
       size_t o = (size_t(y) * W + x) * 4;
       if(out_rgba32f)
       {

@@ -77,6 +77,8 @@ struct vkrt_ctx
   int     W = 0, H = 0;
   float4* dToneF = nullptr;
   uchar4* dTone8 = nullptr;
+  float4* dMips = nullptr;  // auto-exposure mip pyramid (levels 1..n)
+  size_t  mipCapacity = 0;
 
   // wavefront
   Wavefront wf{};
@@ -253,7 +255,7 @@ int vkrt_destroy(vkrt_ctx* ctx)
   cudaFree(ctx->dEnv); cudaFree(ctx->dEnvAccel);
   cudaFree(ctx->dPixelOfLocal);
   if(ctx->ownsImage) cudaFree(ctx->image);
-  cudaFree(ctx->dToneF); cudaFree(ctx->dTone8);
+  cudaFree(ctx->dToneF); cudaFree(ctx->dTone8); cudaFree(ctx->dMips);
   cudaFree(ctx->dStats);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -627,15 +629,42 @@ int vkrt_output_read(vkrt_ctx* ctx, float* host)
 static int tonemapCommon(vkrt_ctx* ctx, const Tonemapper* tm, float* hostF, uint8_t* host8)
 {
   if(!ctx || !tm || !ctx->image) return VKRT_ERR_STATE;
-  if(tm->autoExposure != 0)
-    return fail(ctx, VKRT_ERR_INVALID, "tonemap: autoExposure (mip-pyramid luminance) is not implemented yet");
   cudaSetDevice(ctx->device);
   const size_t n = (size_t)ctx->W * ctx->H;
+  MipView mips{};
+  if(tm->autoExposure & 1)
+  {
+    // RenderOutput::genMipmap (src/render_output.cpp:188-193): the full chain, level 0 is the accumulation image
+    size_t total = 0;
+    int    w = ctx->W, h = ctx->H, levels = 1;
+    while(w > 1 || h > 1) { w = std::max(1, w >> 1); h = std::max(1, h >> 1); total += (size_t)w * h; levels++; }
+    if(levels > 16)
+      return fail(ctx, VKRT_ERR_INVALID, "tonemap: image too large for the mip chain");
+    if(total > ctx->mipCapacity)
+    {
+      cudaFree(ctx->dMips);
+      ctx->dMips = nullptr;
+      CTX_CHECK(cudaMalloc(&ctx->dMips, std::max<size_t>(total, 1) * sizeof(float4)));
+      ctx->mipCapacity = total;
+    }
+    mips.level[0] = ctx->image; mips.w[0] = ctx->W; mips.h[0] = ctx->H;
+    float4* dst = ctx->dMips;
+    for(int l = 1; l < levels; l++)
+    {
+      mips.w[l] = std::max(1, mips.w[l - 1] >> 1);
+      mips.h[l] = std::max(1, mips.h[l - 1] >> 1);
+      launchMipDown(ctx->stream, mips.level[l - 1], mips.w[l - 1], mips.h[l - 1], dst, mips.w[l], mips.h[l]);
+      ctx->stats.kernel_launches++;
+      mips.level[l] = dst;
+      dst += (size_t)mips.w[l] * mips.h[l];
+    }
+    mips.count = levels;
+  }
   if(hostF && !ctx->dToneF) CTX_CHECK(cudaMalloc(&ctx->dToneF, n * sizeof(float4)));
   if(host8 && !ctx->dTone8) CTX_CHECK(cudaMalloc(&ctx->dTone8, n * sizeof(uchar4)));
   {
     ScopedTimer t(ctx, true, T_TONEMAP);
-    launchTonemap(ctx->stream, ctx->image, ctx->W, ctx->H, *tm, hostF ? ctx->dToneF : nullptr, host8 ? ctx->dTone8 : nullptr);
+    launchTonemap(ctx->stream, ctx->image, ctx->W, ctx->H, *tm, mips, hostF ? ctx->dToneF : nullptr, host8 ? ctx->dTone8 : nullptr);
   }
   ctx->stats.kernel_launches++;
   if(hostF) CTX_CHECK(cudaMemcpyAsync(hostF, ctx->dToneF, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));

@@ -60,7 +60,14 @@ void launchShade(cudaStream_t s, const SceneView& scene, const Wavefront& wf, co
 void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, int numSMs);
 void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, int numSMs);
 void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats);
-void launchTonemap(cudaStream_t s, const float4* image, int w, int h, const Tonemapper& tm, float4* outF, uchar4* out8);
+struct MipView  // RGBA32F mip pyramid of the accumulation image (level 0 = the image itself)
+{
+  const float4* level[16];
+  int           w[16], h[16];
+  int           count;
+};
+void launchMipDown(cudaStream_t s, const float4* src, int sw, int sh, float4* dst, int dw, int dh);
+void launchTonemap(cudaStream_t s, const float4* image, int w, int h, const Tonemapper& tm, const MipView& mips, float4* outF, uchar4* out8);
 
 // vkrt_host.cpp
 void buildEnvAccelHost(const float* rgba, uint32_t w, uint32_t h, EnvAccel* out, float* integral, float* average);

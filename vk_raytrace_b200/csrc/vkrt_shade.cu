@@ -619,8 +619,36 @@ VKRT_D float3 toneMapUncharted(float3 color)
   float3 whiteScale = f3(1.0f) / uncharted2Impl(f3(W));
   return linearTosRGB(color * whiteScale);
 }
+// One level of RenderOutput::genMipmap (src/render_output.cpp:188-193): vkCmdBlitImage with VK_FILTER_LINEAR from level k to
+// level k+1 (extent max(1, size >> 1)): source sampled at u = (x + 0.5) * srcW / dstW, linear, clamp-to-edge.
+__global__ void __launch_bounds__(256) mipDownKernel(const float4* __restrict__ src, int sw, int sh, float4* __restrict__ dst, int dw, int dh)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= dw * dh)
+    return;
+  const int   x = i % dw, y = i / dw;
+  const float u = ((float)x + 0.5f) * ((float)sw / (float)dw) - 0.5f, v = ((float)y + 0.5f) * ((float)sh / (float)dh) - 0.5f;
+  const float x0f = floorf(u), y0f = floorf(v), ax = u - x0f, ay = v - y0f;
+  const int   x0 = min(sw - 1, max(0, (int)x0f)), x1 = min(sw - 1, max(0, (int)x0f + 1));
+  const int   y0 = min(sh - 1, max(0, (int)y0f)), y1 = min(sh - 1, max(0, (int)y0f + 1));
+  const float4 c00 = src[(size_t)y0 * sw + x0], c10 = src[(size_t)y0 * sw + x1], c01 = src[(size_t)y1 * sw + x0], c11 = src[(size_t)y1 * sw + x1];
+  const float4 top = c00 * (1.0f - ax) + c10 * ax, bot = c01 * (1.0f - ax) + c11 * ax;
+  dst[i] = top * (1.0f - ay) + bot * ay;
+}
+
+// NEAREST fetch of a mip level (default VkSamplerCreateInfo of the post pass, src/render_output.cpp:96-98)
+VKRT_D float3 mipFetch(const MipView& m, float2 uv, int lod)
+{
+  lod = min(max(lod, 0), m.count - 1);
+  const int w = m.w[lod], h = m.h[lod];
+  const int x = min(w - 1, max(0, (int)floorf(uv.x * (float)w))), y = min(h - 1, max(0, (int)floorf(uv.y * (float)h)));
+  return f3(m.level[lod][(size_t)y * w + x]);
+}
+VKRT_D float postLuminance(float3 c) { return dot(c, f3(0.2126f, 0.7152f, 0.0722f)); }
+VKRT_D float xyzY(float3 rgb) { return (0.3575761f * rgb.x + 0.7151522f * rgb.y) + 0.1191920f * rgb.z; }  // post.frag:57 (column-major quirk)
+
 __global__ void __launch_bounds__(256) tonemapKernel(const float4* __restrict__ image, int W, int H, const __grid_constant__ Tonemapper tm,
-                                                     float4* __restrict__ outF, uchar4* __restrict__ out8)
+                                                     const __grid_constant__ MipView mips, float4* __restrict__ outF, uchar4* __restrict__ out8)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= W * H)
@@ -630,7 +658,39 @@ __global__ void __launch_bounds__(256) tonemapKernel(const float4* __restrict__ 
   const int sx = min(W - 1, max(0, (int)floorf(uvCoords.x * tm.zoom * (float)W)));
   const int sy = min(H - 1, max(0, (int)floorf(uvCoords.y * tm.zoom * (float)H)));
   const float4 hdr = image[(size_t)sy * W + sx];
-  float3 color = toneMapUncharted(f3(hdr) * tm.avgLum);
+  float3 hdrRgb = f3(hdr);
+  if((tm.autoExposure & 1) && mips.count > 0)
+  {
+    // post.frag:101-111: average = the 1x1 top mip; toneExposure (post.frag:64-70) or toneLocalExposure (:72-95)
+    const float logAvgLum = postLuminance(mipFetch(mips, f2(0.5f, 0.5f), 20));
+    const float XYZy      = xyzY(hdrRgb);
+    const float Y         = (tm.key / logAvgLum) * XYZy;
+    float       Yd;
+    if((tm.autoExposure >> 1) & 1)
+    {
+      const float2 uvz    = f2(uvCoords.x * tm.zoom, uvCoords.y * tm.zoom);
+      const float  factor = tm.key / logAvgLum;
+      float        La = 0.f, sc = 1.f;
+      for(int l = 0; l < 7; ++l)
+      {
+        const float v1 = postLuminance(mipFetch(mips, uvz, l)) * factor;
+        const float v2 = postLuminance(mipFetch(mips, uvz, l + 1)) * factor;
+        if(fabsf(v1 - v2) / ((tm.key * 4.0f / (sc * sc)) + v1) > 0.05f)  // 4 = pow(2, phi), phi = 2
+        {
+          La = v1;
+          break;
+        }
+        else
+          La = v2;
+        sc *= 2.f;
+      }
+      Yd = Y / (1.0f + La);
+    }
+    else
+      Yd = (Y * (1.0f + Y / (tm.Ywhite * tm.Ywhite))) / (1.0f + Y);
+    hdrRgb = hdrRgb / XYZy * Yd;
+  }
+  float3 color = toneMapUncharted(hdrRgb * tm.avgLum);
   if(tm.dither > 0)
   {
     uint32_t rx = (uint32_t)x, ry = (uint32_t)y, rz = 0u;
@@ -696,9 +756,13 @@ void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp
 {
   accumulateKernel<<<(wf.numLocalPixels + 255) / 256, 256, 0, s>>>(wf, fp, image);
 }
-void launchTonemap(cudaStream_t s, const float4* image, int w, int h, const Tonemapper& tm, float4* outF, uchar4* out8)
+void launchMipDown(cudaStream_t s, const float4* src, int sw, int sh, float4* dst, int dw, int dh)
 {
-  tonemapKernel<<<(w * h + 255) / 256, 256, 0, s>>>(image, w, h, tm, outF, out8);
+  mipDownKernel<<<(dw * dh + 255) / 256, 256, 0, s>>>(src, sw, sh, dst, dw, dh);
+}
+void launchTonemap(cudaStream_t s, const float4* image, int w, int h, const Tonemapper& tm, const MipView& mips, float4* outF, uchar4* out8)
+{
+  tonemapKernel<<<(w * h + 255) / 256, 256, 0, s>>>(image, w, h, tm, mips, outF, out8);
 }
 
 }  // namespace vkrt
