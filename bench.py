@@ -78,9 +78,10 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-def algorithmic_bytes(rays, nodes, tris):
-    """per ray 32 B ray + 16 B hit + 64 B per node + 48 B per triangle (single-level BVH: no instance term)."""
-    return 48 * rays + 64 * nodes + 48 * tris
+def algorithmic_bytes(rays, nodes, tris, node_bytes=64):
+    """per ray 32 B ray + 16 B hit + node_bytes per node + 48 B per triangle (single-level BVH: no instance term).
+    node_bytes is what the traversal kernel actually fetches per node: 32 (16-bit grid boxes, default) or 64 (fp32 boxes)."""
+    return 48 * rays + node_bytes * nodes + 48 * tris
 
 
 def measured_peaks():
@@ -189,7 +190,7 @@ def main():
     opts = S.RenderOpts()
     opts.shard_rank, opts.shard_count = (rank, world) if use_dist else (0, 1)
     opts.frames_in_flight = args.frames_in_flight
-    opts.profile = 1
+    opts.profile = 0    # timed region: no per-kernel events, so shadow(b) overlaps closest(b+1) on the library's second stream
 
     def barrier():
         torch.cuda.synchronize()
@@ -238,6 +239,14 @@ def main():
     else:
         total_ms, total_rays = my_ms, rays
     launches = int(s.kernel_launches)
+    # per-kernel device time: the same frames again with per-kernel CUDA events (kernels serialised, untimed pass)
+    opts_p = S.RenderOpts()
+    opts_p.shard_rank, opts_p.shard_count, opts_p.profile = opts.shard_rank, opts.shard_count, 1
+    opts_p.frames_in_flight = args.frames_in_flight
+    ctx.reset_stats()
+    st.frame = args.warmup
+    ctx.render(st, args.steps, opts_p)
+    s = ctx.stats()
     kernel_ms = dict(raygen=s.ms_raygen, trace_closest=s.ms_trace_closest, trace_shadow=s.ms_trace_shadow, shade=s.ms_shade,
                      accumulate=s.ms_accumulate)
 
@@ -251,8 +260,9 @@ def main():
     ctx.render(st, args.steps, opts_c)
     sc = ctx.stats()
     c_nodes, c_tris = sc.nodes_visited - sc.shadow_nodes_visited, sc.tris_tested - sc.shadow_tris_tested
-    bytes_closest = algorithmic_bytes(sc.closest_rays, c_nodes, c_tris)
-    bytes_shadow = algorithmic_bytes(sc.shadow_rays, sc.shadow_nodes_visited, sc.shadow_tris_tested)
+    node_bytes = int(sc.node_bytes) or 64
+    bytes_closest = algorithmic_bytes(sc.closest_rays, c_nodes, c_tris, node_bytes)
+    bytes_shadow = algorithmic_bytes(sc.shadow_rays, sc.shadow_nodes_visited, sc.shadow_tris_tested, node_bytes)
     ach_closest = bytes_closest / max(kernel_ms["trace_closest"], 1e-9) / 1e6   # GB/s
     ach_shadow = bytes_shadow / max(kernel_ms["trace_shadow"], 1e-9) / 1e6
     traffic = None
@@ -263,19 +273,19 @@ def main():
         except Exception:
             traffic = None
     # the resource that actually binds the traversal: the L1 data pipe serves one cache-line wavefront per clock per SM and a
-    # node step of a lane is two of them (64-B node fetched as two 32-B halves), see profiles/README.md
+    # node step of a lane costs node_bytes / 32 of them (32-B quantised node: one; fp32 node: two), see profiles/README.md
     sm_clk = (sampler.summary()["sm_mhz"] or 1965.0) * 1e6
     steps_per_s = c_nodes / max(kernel_ms["trace_closest"], 1e-9) * 1e3
-    l1_peak = 148 * sm_clk * 0.5
+    l1_peak = 148 * sm_clk * (32.0 / node_bytes)
     roofline = {"kernel": "traceKernel<CLOSEST>", "bound": "hbm", "achieved": ach_closest, "peak": peak, "unit": "GB/s", "frac": ach_closest / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "per_ray": {"nodes": c_nodes / max(1, sc.closest_rays), "tris": c_tris / max(1, sc.closest_rays),
+                "per_ray": {"node_bytes": node_bytes, "nodes": c_nodes / max(1, sc.closest_rays), "tris": c_tris / max(1, sc.closest_rays),
                             "bytes": bytes_closest / max(1, sc.closest_rays)},
                 "shadow_kernel": {"achieved": ach_shadow, "frac": ach_shadow / peak,
                                   "nodes_per_ray": sc.shadow_nodes_visited / max(1, sc.shadow_rays),
                                   "tris_per_ray": sc.shadow_tris_tested / max(1, sc.shadow_rays)},
                 "l1_gather": {"achieved_gsteps_per_s": steps_per_s / 1e9, "peak_gsteps_per_s": l1_peak / 1e9, "frac": steps_per_s / l1_peak,
-                              "what": "BVH node steps/s vs 148 SMs x SM clock x 0.5 (one L1 wavefront per clock per SM, two per 64-B node)"},
+                              "what": "BVH node steps/s vs 148 SMs x SM clock x (32 B / node bytes): the L1 serves one 32-byte-per-lane wavefront per clock per SM"},
                 "note": "algorithmic bytes (SURVEY 8d) / summed CUDA-event kernel time.  For L2-resident scenes (this one: 30 MB BVH) the "
                         "algorithmic rate exceeds the HBM peak because node traffic is served by L1/L2; DRAM traffic (`traffic`, ncu) is only "
                         "the ray/hit streams.  The kernel is bound by L1 gather wavefronts (l1_gather), not by HBM; the HBM-resident case is "

@@ -74,14 +74,16 @@ typedef struct vkrt_stats
   double   ms_tonemap;
   double   ms_build;        /* last vkrt_scene_commit (transform + LBVH build)    */
   uint32_t num_triangles;   /* world-space triangles in the BVH                   */
-  uint32_t num_bvh_nodes;   /* 64-byte BVH2 nodes                                 */
+  uint32_t num_bvh_nodes;   /* BVH2 nodes (node_bytes each as read by the trace kernels) */
   uint32_t num_instances;   /* TLAS-equivalent nodes (src/accelstruct.cpp:132)    */
   uint32_t has_non_opaque;  /* any instance that is not FORCE_OPAQUE              */
   uint64_t shadow_nodes_visited; /* the any-hit kernel's share of nodes_visited   */
   uint64_t shadow_tris_tested;   /* the any-hit kernel's share of tris_tested     */
   uint32_t bvh_max_depth;   /* depth of the BVH2 (traversal stack bound)          */
+  uint32_t node_bytes;      /* bytes per node fetched by the trace kernels: 32 (16-bit grid boxes, default) or 64 (fp32) */
+  uint32_t bvh_width;       /* children per node of the active traversal kernel: 2 (default) or 4 */
   uint32_t _pad;
-  double   reserved[5];
+  double   reserved[4];
 } vkrt_stats;
 
 /* ---- context ---------------------------------------------------------- */

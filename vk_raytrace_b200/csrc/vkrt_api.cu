@@ -44,6 +44,8 @@ struct vkrt_ctx
 {
   int          device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // any-hit kernels, overlapped with the next bounce's closest-hit kernel
+  cudaEvent_t  evShade = nullptr, evShadow = nullptr;
   int          numSMs = 148;
   std::string  err;
 
@@ -120,7 +122,7 @@ static void freeScene(vkrt_ctx* c)
   cudaFree(c->dMat); cudaFree(c->dLights); cudaFree(c->dTexDescs);
   for(auto p : c->dTexData) cudaFree(p);
   c->dTexData.clear();
-  cudaFree(c->bvh.nodes); cudaFree(c->bvh.triInfo); cudaFree(c->bvh.triShade);
+  cudaFree(c->bvh.nodes); cudaFree(c->bvh.qnodes); cudaFree(c->bvh.cnodes); cudaFree(c->bvh.wnodes); cudaFree(c->bvh.triInfo); cudaFree(c->bvh.triShade);
   c->dVerts = nullptr; c->dIdx = nullptr; c->dGeo = nullptr; c->dInst = nullptr; c->dInstTriOffset = nullptr;
   c->dMat = nullptr; c->dLights = nullptr; c->dTexDescs = nullptr;
   c->bvh = BvhResult{};
@@ -221,6 +223,9 @@ int vkrt_create(int cuda_device, vkrt_ctx** out_ctx)
     delete ctx;
     return VKRT_ERR_CUDA;
   }
+  cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->evShade, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->evShadow, cudaEventDisableTiming);
   cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, cuda_device);
   if(cudaMalloc(&ctx->dStats, sizeof(TraceStats)) != cudaSuccess)
   {
@@ -257,6 +262,8 @@ int vkrt_destroy(vkrt_ctx* ctx)
   if(ctx->ownsImage) cudaFree(ctx->image);
   cudaFree(ctx->dToneF); cudaFree(ctx->dTone8); cudaFree(ctx->dMips);
   cudaFree(ctx->dStats);
+  cudaEventDestroy(ctx->evShade); cudaEventDestroy(ctx->evShadow);
+  cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return VKRT_OK;
@@ -394,6 +401,8 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
     uint32_t                 fl  = 0;
     if(mat.alphaMode == 0 || (mat.pbrBaseColorFactor[3] == 1.0f && mat.pbrBaseColorTexture == -1))
       fl |= TRI_OPAQUE;
+    if(getenv("VKRT_DEBUG_FORCE_OPAQUE"))
+      fl |= TRI_OPAQUE;  // profiling aid only: the image changes (alpha-tested geometry becomes solid)
     if(mat.doubleSided == 1)
       fl |= TRI_CULL_DISABLE;
     const float* w = n.world;
@@ -478,6 +487,17 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
     CTX_CHECK(cudaMemcpy(ctx->bvh.tris, sorted.data(), sorted.size() * sizeof(float), cudaMemcpyHostToDevice));
     ctx->bvh.maxDepth = depth;
   }
+  if(!quantizeBvh(ctx->stream, ctx->bvh, berr, &launches))
+  {
+    ctx->err = "scene_commit: BVH node quantisation failed: " + berr;
+    return VKRT_ERR_CUDA;
+  }
+  if(!collapseBvhWide(ctx->stream, ctx->bvh, berr, &launches))
+  {
+    ctx->err = "scene_commit: BVH4 collapse failed: " + berr;
+    return VKRT_ERR_CUDA;
+  }
+  ctx->stats.kernel_launches += 1 + (uint64_t)ctx->bvh.wideDepth;
   cudaEventRecord(e1, ctx->stream);
   CTX_CHECK(cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
@@ -487,6 +507,10 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
   ctx->stats.ms_build       = ms;
   ctx->stats.num_triangles  = (uint32_t)totalTris;
   ctx->stats.num_bvh_nodes  = ctx->bvh.numNodes;
+  ctx->stats.node_bytes     = (uint32_t)traceNodeBytes();
+  ctx->stats.bvh_width      = (uint32_t)traceBvhWidth();
+  if(traceBvhWidth() == 4)
+    ctx->stats.num_bvh_nodes = ctx->bvh.numWideNodes;
   ctx->stats.num_instances  = (uint32_t)inst.size();
   ctx->stats.has_non_opaque = nonOpaque ? 1u : 0u;
 
@@ -513,6 +537,11 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
   }
   SceneView& v   = ctx->view;
   v.nodes        = ctx->bvh.nodes;
+  v.qnodes       = ctx->bvh.qnodes;
+  v.cnodes       = ctx->bvh.cnodes;
+  v.wnodes       = ctx->bvh.wnodes;
+  v.gridOrigin   = make_float3(ctx->bvh.gridOrigin[0], ctx->bvh.gridOrigin[1], ctx->bvh.gridOrigin[2]);
+  v.gridInv      = make_float3(ctx->bvh.gridInv[0], ctx->bvh.gridInv[1], ctx->bvh.gridInv[2]);
   v.tris         = ctx->bvh.tris;
   v.triInfo      = ctx->bvh.triInfo;
   v.triShade     = ctx->bvh.triShade;
@@ -756,6 +785,9 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
   const int  rank     = shards > 1 ? o.shard_rank : 0;
   const bool counting = o.count_traversal != 0;
   const bool timing   = o.profile != 0;  // per-kernel CUDA-event timing
+  // per-kernel timing needs the kernels one after the other; otherwise shadow(b) overlaps closest(b+1) on a second stream
+  static const bool overlapEnv = []() { const char* e = getenv("VKRT_OVERLAP"); return !e || atoi(e) != 0; }();
+  const bool overlap  = overlapEnv && !timing;
   if(rank < 0 || rank >= shards)
     return fail(ctx, VKRT_ERR_INVALID, "render: shard_rank out of range");
 
@@ -795,7 +827,8 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
       ctx->stats.kernel_launches++;
       for(int depth = 0; depth < state->maxDepth; depth++)
       {
-        fp.depth = depth;
+        fp.depth      = depth;
+        wf.shadowSlot = (uint32_t)(depth & 1);
         TraceLaunch L{};
         L.rayO = wf.rayO; L.rayD = wf.rayD; L.queue = wf.queueCur; L.count = wf.counters + 0; L.cursor = wf.counters + 3;
         L.hit = wf.hit; L.stats = dstats;
@@ -803,13 +836,26 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
           ScopedTimer t(ctx, timing, T_CLOSEST);
           launchTraceClosest(ctx->stream, ctx->view, L, counting, ctx->numSMs);
         }
+        if(overlap && depth > 0)
+          cudaStreamWaitEvent(ctx->stream, ctx->evShadow, 0);  // shade(b) adds to the radiance shadow(b-1) resolves into
         {
           ScopedTimer t(ctx, timing, T_SHADE);
           launchShade(ctx->stream, ctx->view, wf, fp, dstats, ctx->numSMs);
         }
         TraceLaunch S{};
-        S.rayO = wf.shO; S.rayD = wf.shD; S.queue = nullptr; S.count = wf.counters + 2; S.cursor = wf.counters + 4;
+        S.rayO = wf.shO; S.rayD = wf.shD; S.queue = nullptr;
+        S.count = wf.counters + (wf.shadowSlot ? 5 : 2); S.cursor = wf.counters + (wf.shadowSlot ? 6 : 4);
         S.shC = wf.shC; S.rad = wf.rad; S.stats = dstats;
+        if(overlap)
+        {
+          // the any-hit kernel of this bounce runs beside the closest-hit kernel of the next one: the tail of either
+          // persistent kernel is filled by the other's CTAs
+          cudaEventRecord(ctx->evShade, ctx->stream);
+          cudaStreamWaitEvent(ctx->stream2, ctx->evShade, 0);
+          launchTraceShadow(ctx->stream2, ctx->view, S, counting, ctx->numSMs);
+          cudaEventRecord(ctx->evShadow, ctx->stream2);
+        }
+        else
         {
           ScopedTimer t(ctx, timing, T_SHADOW);
           launchTraceShadow(ctx->stream, ctx->view, S, counting, ctx->numSMs);
@@ -818,6 +864,8 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
         std::swap(wf.queueCur, wf.queueNext);
         ctx->stats.kernel_launches += 4;
       }
+      if(overlap && state->maxDepth > 0)
+        cudaStreamWaitEvent(ctx->stream, ctx->evShadow, 0);
       {
         ScopedTimer t(ctx, timing, T_ACCUM);
         launchFinishSample(ctx->stream, wf, fp, ctx->numSMs);
@@ -953,7 +1001,7 @@ int vkrt_reset_stats(vkrt_ctx* ctx)
   ctx->stats      = vkrt_stats{};
   ctx->stats.ms_build = keep.ms_build; ctx->stats.num_triangles = keep.num_triangles; ctx->stats.num_bvh_nodes = keep.num_bvh_nodes;
   ctx->stats.num_instances = keep.num_instances; ctx->stats.has_non_opaque = keep.has_non_opaque;
-  ctx->stats.bvh_max_depth = keep.bvh_max_depth;
+  ctx->stats.bvh_max_depth = keep.bvh_max_depth; ctx->stats.node_bytes = keep.node_bytes; ctx->stats.bvh_width = keep.bvh_width;
   return VKRT_OK;
 }
 

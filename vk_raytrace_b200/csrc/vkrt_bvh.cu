@@ -336,6 +336,235 @@ __global__ void emptySceneKernel(float4* nodes)
     }                                                                                                                  \
   } while(0)
 
+// 32-byte nodes.  Per-lane node gathers are bound by L1 wavefronts (one 32-byte request per lane per wavefront), so a
+// node that fits one 256-bit load halves the cost of a traversal step.  The two child boxes are stored on a 16-bit grid
+// G(p) = (p - gridOrigin) * gridInv laid over the root box with an 8-cell margin:
+//   word 0..2: child 0  x,y,z  (lo | hi << 16)      word 3..5: child 1      word 6,7: child references (as in the fp32 node)
+// lo is rounded down and hi up after padding by 1.0625 cells: the trace kernel evaluates the slab planes as
+// fma(2^23 + q, 1/d_g, t0 - (o_g + 2^23) / d_g), whose rounding moves a plane by at most 0.5 (o_g + 2^23 rounds to a whole
+// cell) + 0.504 (the product) + 2^-7 (evaluating G in fp32) cells, so the padded box always contains the true one and the
+// box test stays a conservative filter: hits are decided by the triangle test alone, results are identical to the fp32 nodes.
+__global__ void quantizeNodesKernel(const float4* __restrict__ nodes, uint32_t numNodes, float3 origin, float3 inv, uint4* __restrict__ q)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= numNodes)
+    return;
+  const float4 n0 = nodes[4ull * i], n1 = nodes[4ull * i + 1], n2 = nodes[4ull * i + 2], n3 = nodes[4ull * i + 3];
+  auto lo = [](float v, float o, float s) { return (uint32_t)min(65535, max(0, (int)floorf((v - o) * s - 1.0625f))); };
+  auto hi = [](float v, float o, float s) { return (uint32_t)min(65535, max(0, (int)ceilf((v - o) * s + 1.0625f))); };
+  uint4 a, b;
+  a.x = lo(n0.x, origin.x, inv.x) | (hi(n0.y, origin.x, inv.x) << 16);
+  a.y = lo(n0.z, origin.y, inv.y) | (hi(n0.w, origin.y, inv.y) << 16);
+  a.z = lo(n2.x, origin.z, inv.z) | (hi(n2.y, origin.z, inv.z) << 16);
+  a.w = lo(n1.x, origin.x, inv.x) | (hi(n1.y, origin.x, inv.x) << 16);
+  b.x = lo(n1.z, origin.y, inv.y) | (hi(n1.w, origin.y, inv.y) << 16);
+  b.y = lo(n2.z, origin.z, inv.z) | (hi(n2.w, origin.z, inv.z) << 16);
+  b.z = __float_as_uint(n3.x);
+  b.w = __float_as_uint(n3.y);
+  q[2ull * i]     = a;
+  q[2ull * i + 1] = b;
+}
+
+// Centre / half-extent copy of the fp32 nodes, the layout the default traversal kernel reads:
+//   m0 = (c0.cx, c0.ex, c0.cy, c0.ey)  m1 = (c1.cx, c1.ex, c1.cy, c1.ey)  m2 = (c0.cz, c0.ez, c1.cz, c1.ez)  m3 = references
+// With it the slab test is t_near/far = fma(-/+e, |1/d|, fma(c, 1/d, -o/d)): nine FMA-pipe instructions per box and no
+// per-axis min/max on the (half-rate, saturated) ALU pipe.  e is padded so that [c-e, c+e] contains the fp32 box and the
+// rounding of c/d - o/d (a plane displacement of at most 2^-24 of the coordinate magnitude) can never cut a box short.
+__global__ void centerNodesKernel(const float4* __restrict__ nodes, uint32_t numNodes, float4* __restrict__ out)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= numNodes)
+    return;
+  const float4 n0 = nodes[4ull * i], n1 = nodes[4ull * i + 1], n2 = nodes[4ull * i + 2], n3 = nodes[4ull * i + 3];
+  auto ce = [](float lo, float hi, float& c, float& e) {
+    c = 0.5f * lo + 0.5f * hi;
+    e = fmaxf(hi - c, c - lo);
+    e = (e + (fabsf(c) + e) * 4.8e-7f) * 1.000001f;
+  };
+  float4 m0, m1, m2;
+  ce(n0.x, n0.y, m0.x, m0.y); ce(n0.z, n0.w, m0.z, m0.w);
+  ce(n1.x, n1.y, m1.x, m1.y); ce(n1.z, n1.w, m1.z, m1.w);
+  ce(n2.x, n2.y, m2.x, m2.y); ce(n2.z, n2.w, m2.z, m2.w);
+  out[4ull * i] = m0; out[4ull * i + 1] = m1; out[4ull * i + 2] = m2; out[4ull * i + 3] = n3;
+}
+
+bool quantizeBvh(cudaStream_t stream, BvhResult& bvh, std::string& err, uint64_t* launches)
+{
+  float          root[16];
+  const uint32_t n = std::max<uint32_t>(bvh.numNodes, 1u);
+  cudaFree(bvh.qnodes);
+  bvh.qnodes = nullptr;
+  CK(cudaMalloc(&bvh.qnodes, 32ull * n));
+  CK(cudaMemcpyAsync(root, bvh.nodes, sizeof(root), cudaMemcpyDeviceToHost, stream));
+  CK(cudaStreamSynchronize(stream));
+  {
+    // root box = union of the root's child boxes (layout of emitKernel)
+    const float lo[3] = {std::min(root[0], root[4]), std::min(root[2], root[6]), std::min(root[8], root[10])};
+    const float hi[3] = {std::max(root[1], root[5]), std::max(root[3], root[7]), std::max(root[9], root[11])};
+    float       maxExt = 0.f;
+    for(int a = 0; a < 3; a++)
+      maxExt = std::max(maxExt, hi[a] - lo[a]);
+    if(!(maxExt > 0.f) || !std::isfinite(maxExt))
+      maxExt = 1.f;
+    for(int a = 0; a < 3; a++)
+    {
+      // a flat axis still gets cells of a useful size, so that ray origins stay within range of the 2^23 bias
+      const float ext  = std::max(std::isfinite(hi[a] - lo[a]) ? hi[a] - lo[a] : 0.f, 1e-3f * maxExt);
+      const float cell = ext / 65500.0f;
+      bvh.gridOrigin[a] = (std::isfinite(lo[a]) ? lo[a] : 0.f) - 8.0f * cell;
+      bvh.gridInv[a]    = 1.0f / cell;
+    }
+  }
+  quantizeNodesKernel<<<(n + 255) / 256, 256, 0, stream>>>(bvh.nodes, n, make_float3(bvh.gridOrigin[0], bvh.gridOrigin[1], bvh.gridOrigin[2]),
+                                                           make_float3(bvh.gridInv[0], bvh.gridInv[1], bvh.gridInv[2]), bvh.qnodes);
+  cudaFree(bvh.cnodes);
+  bvh.cnodes = nullptr;
+  CK(cudaMalloc(&bvh.cnodes, 64ull * n));
+  centerNodesKernel<<<(n + 255) / 256, 256, 0, stream>>>(bvh.nodes, n, bvh.cnodes);
+  if(launches) (*launches) += 2;
+  CK(cudaGetLastError());
+  return true;
+fail:
+  cudaFree(bvh.qnodes); cudaFree(bvh.cnodes);
+  bvh.qnodes = nullptr;
+  bvh.cnodes = nullptr;
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------------
+// BVH4: the binary tree collapsed into 4-wide nodes, boxes on the same 16-bit grid (64 bytes per node):
+//   word 3k..3k+2: child k  x,y,z (lo | hi << 16), k = 0..3      word 12..15: child references
+// A reference is a BVH4 node index, a leaf code (kLeafBit, as in the binary tree) or kEmptyRef; empty slots carry
+// an inverted box (lo 65535, hi 0) that no ray can enter.  One traversal step tests four boxes behind two 256-bit
+// loads, and a ray needs about half as many dependent steps as in the binary tree.
+// Built level by level from the root: each 4-wide node starts from the two children of its binary node and
+// repeatedly opens the inner child with the largest surface area until it has four children.
+constexpr uint32_t kEmptyRef = 0xffffffffu;  // also has kLeafBit set: count field 7, never produced by emitKernel for a real leaf first index
+
+struct WideCand
+{
+  float    lo[3], hi[3];
+  uint32_t ref;
+};
+
+__global__ void collapseWideKernel(const float4* __restrict__ nodes, uint32_t* __restrict__ src, uint32_t begin, uint32_t end,
+                                   uint32_t* __restrict__ count, float3 origin, float3 inv, uint4* __restrict__ wide)
+{
+  const uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= end)
+    return;
+  WideCand c[4];
+  int      n = 0;
+  auto open = [&](uint32_t node, int slot) {
+    const float4 n0 = nodes[4ull * node], n1 = nodes[4ull * node + 1], n2 = nodes[4ull * node + 2], n3 = nodes[4ull * node + 3];
+    WideCand a, b;
+    a.lo[0] = n0.x; a.hi[0] = n0.y; a.lo[1] = n0.z; a.hi[1] = n0.w; a.lo[2] = n2.x; a.hi[2] = n2.y; a.ref = __float_as_uint(n3.x);
+    b.lo[0] = n1.x; b.hi[0] = n1.y; b.lo[1] = n1.z; b.hi[1] = n1.w; b.lo[2] = n2.z; b.hi[2] = n2.w; b.ref = __float_as_uint(n3.y);
+    c[slot] = a;
+    c[n++]  = b;
+  };
+  n = 1;  // slot 0 is filled by the first open()
+  open(src[i], 0);
+  while(n < 4)
+  {
+    int   pick = -1;
+    float best = -1.f;
+    for(int k = 0; k < n; k++)
+    {
+      if(c[k].ref & kLeafBit)
+        continue;
+      const float dx = c[k].hi[0] - c[k].lo[0], dy = c[k].hi[1] - c[k].lo[1], dz = c[k].hi[2] - c[k].lo[2];
+      const float area = dx * dy + dy * dz + dz * dx;
+      if(area > best)
+      {
+        best = area;
+        pick = k;
+      }
+    }
+    if(pick < 0)
+      break;
+    open(c[pick].ref, pick);
+  }
+  // inner children become 4-wide nodes of the next level
+  int inner = 0;
+  for(int k = 0; k < n; k++)
+    inner += (c[k].ref & kLeafBit) ? 0 : 1;
+  uint32_t base = inner ? atomicAdd(count, (uint32_t)inner) : 0u;
+  uint32_t w[16];
+  auto qlo = [](float v, float o, float s) { return (uint32_t)min(65535, max(0, (int)floorf((v - o) * s - 1.0625f))); };
+  auto qhi = [](float v, float o, float s) { return (uint32_t)min(65535, max(0, (int)ceilf((v - o) * s + 1.0625f))); };
+  for(int k = 0; k < 4; k++)
+  {
+    if(k < n)
+    {
+      w[3 * k + 0] = qlo(c[k].lo[0], origin.x, inv.x) | (qhi(c[k].hi[0], origin.x, inv.x) << 16);
+      w[3 * k + 1] = qlo(c[k].lo[1], origin.y, inv.y) | (qhi(c[k].hi[1], origin.y, inv.y) << 16);
+      w[3 * k + 2] = qlo(c[k].lo[2], origin.z, inv.z) | (qhi(c[k].hi[2], origin.z, inv.z) << 16);
+      if(c[k].ref & kLeafBit)
+        w[12 + k] = c[k].ref;
+      else
+      {
+        src[base]  = c[k].ref;
+        w[12 + k]  = base++;
+      }
+    }
+    else
+    {
+      w[3 * k + 0] = w[3 * k + 1] = w[3 * k + 2] = 0x0000ffffu;  // lo 65535, hi 0
+      w[12 + k]    = kEmptyRef;
+    }
+  }
+  uint4* out = wide + 4ull * i;
+  out[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  out[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  out[2] = make_uint4(w[8], w[9], w[10], w[11]);
+  out[3] = make_uint4(w[12], w[13], w[14], w[15]);
+}
+
+// needs quantizeBvh (grid) first
+bool collapseBvhWide(cudaStream_t stream, BvhResult& bvh, std::string& err, uint64_t* launches)
+{
+  uint32_t *src = nullptr, *count = nullptr;
+  uint32_t  begin = 0, end = 1, levels = 0;
+  const uint32_t n = std::max<uint32_t>(bvh.numNodes, 1u);
+  const float3   origin = make_float3(bvh.gridOrigin[0], bvh.gridOrigin[1], bvh.gridOrigin[2]);
+  const float3   inv    = make_float3(bvh.gridInv[0], bvh.gridInv[1], bvh.gridInv[2]);
+  cudaFree(bvh.wnodes);
+  bvh.wnodes = nullptr;
+  CK(cudaMalloc(&bvh.wnodes, 64ull * n));
+  CK(cudaMalloc(&src, 4ull * n));
+  CK(cudaMalloc(&count, 4));
+  CK(cudaMemsetAsync(src, 0, 4, stream));  // the root of the binary tree is node 0
+  {
+    const uint32_t one = 1;
+    CK(cudaMemcpyAsync(count, &one, 4, cudaMemcpyHostToDevice, stream));
+  }
+  while(begin < end)
+  {
+    collapseWideKernel<<<(end - begin + 127) / 128, 128, 0, stream>>>(bvh.nodes, src, begin, end, count, origin, inv, bvh.wnodes);
+    if(launches) (*launches)++;
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, count, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    begin = end;
+    end   = total;
+    levels++;
+    if(end > n || levels > 4096)
+    {
+      err = "collapseBvhWide: node count out of range";
+      goto fail;
+    }
+  }
+  bvh.numWideNodes = end;
+  bvh.wideDepth    = (int)levels;
+  cudaFree(src); cudaFree(count);
+  return true;
+fail:
+  cudaFree(src); cudaFree(count); cudaFree(bvh.wnodes);
+  bvh.wnodes = nullptr;
+  return false;
+}
+
 // Host driver.  All temporaries are freed before returning; nodes/tris/triInfo are owned by the caller.
 bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* dInstTriOffset, uint32_t numInst, const InstanceData* dGeo,
               uint32_t numTris, int buildMode, BvhResult& out, std::string& err, uint64_t* launches)

@@ -42,7 +42,11 @@ struct TexDesc
 struct SceneView
 {
   // traversal
-  const float4* nodes;     // 4 per node
+  const float4* nodes;     // 4 per node (fp32 boxes, 64 bytes)
+  const float4* cnodes;    // 4 per node (centre / half-extent boxes, 64 bytes): the default traversal format
+  const uint4*  qnodes;    // 2 per node (16-bit grid boxes, 32 bytes): what the trace kernels read by default
+  const uint4*  wnodes;    // 4 per BVH4 node (four 16-bit grid boxes + four references, 64 bytes), VKRT_BVH_WIDTH=4
+  float3        gridOrigin, gridInv;  // G(p) = (p - gridOrigin) * gridInv, see quantizeBvh
   const float4* tris;      // 3 per triangle, leaf order
   const uint2*  triInfo;   // by flattened triangle id: {node(instance), prim}
   const uint4*  triShade;  // by flattened triangle id: 3 x VertexAttributes (6 x uint4) + {instance, material, flags, prim}
@@ -76,7 +80,8 @@ struct Wavefront
   float4*   shC;       // contribution.xyz, path id bits
   uint32_t* queueCur;  // path ids to process this bounce
   uint32_t* queueNext;
-  uint32_t* counters;  // [0] cur count, [1] next count, [2] shadow count, [3] trace cursor, [4] shadow cursor
+  uint32_t* counters;  // [0] cur count, [1] next count, [2] shadow count, [3] trace cursor, [4] shadow cursor, [5]/[6] shadow count/cursor of odd bounces
+  uint32_t  shadowSlot;  // bounce parity: which shadow count/cursor pair this bounce uses (the any-hit kernel of bounce b overlaps bounce b+1)
   const uint32_t* pixelOfLocal;  // local pixel slot -> y*W + x
   uint32_t  numLocalPixels;
   uint32_t  numPaths;  // numLocalPixels * framesInFlight

@@ -22,11 +22,24 @@ struct BvhResult
   uint32_t numNodes = 0;
   uint32_t numTris  = 0;
   int      maxDepth = 0;
+  // 32-byte quantised copy of `nodes` (the format the trace kernels read by default), see quantizeBvh
+  uint4*   qnodes   = nullptr;  // 2 per node
+  float4*  cnodes   = nullptr;  // 4 per node: centre / half-extent form of `nodes` (default traversal format)
+  uint4*   wnodes   = nullptr;  // 4 per BVH4 node (64 bytes), see collapseBvhWide
+  uint32_t numWideNodes = 0;
+  int      wideDepth = 0;
+  float    gridOrigin[3] = {0.f, 0.f, 0.f};
+  float    gridInv[3]    = {1.f, 1.f, 1.f};
 };
 
 // vkrt_bvh.cu
 bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* dInstTriOffset, uint32_t numInst, const InstanceData* dGeo,
               uint32_t numTris, int buildMode, BvhResult& out, std::string& err, uint64_t* launches);
+
+// 64-byte fp32 nodes -> 32-byte nodes: child boxes on a 16-bit grid over the root box (conservatively padded), same topology
+bool quantizeBvh(cudaStream_t stream, BvhResult& bvh, std::string& err, uint64_t* launches);
+// binary tree -> 4-wide nodes on the same grid (call after quantizeBvh)
+bool collapseBvhWide(cudaStream_t stream, BvhResult& bvh, std::string& err, uint64_t* launches);
 
 // vkrt_trace.cu
 struct TraceLaunch
@@ -42,6 +55,8 @@ struct TraceLaunch
   float4*         rad;
   TraceStats*     stats;      // nullptr unless counting
 };
+int  traceBvhWidth();   // 2 or 4: tree width of the active traversal kernel
+int  traceNodeBytes();  // 32 or 64: node format of the active traversal kernel
 void launchTraceClosest(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, bool count, int numSMs);
 void launchTraceShadow(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, bool count, int numSMs);
 void launchTraceAnyProbe(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, int numSMs);

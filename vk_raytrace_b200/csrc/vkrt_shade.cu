@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(256) raygenKernel(const __grid_constant__ Scen
     wf.counters[2] = 0;
     wf.counters[3] = 0;
     wf.counters[4] = 0;
+    wf.counters[5] = 0;
+    wf.counters[6] = 0;
   }
   if(p >= wf.numPaths)
     return;
@@ -531,7 +533,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(cons
     if(lane == 0)
     {
       if(mNext) baseNext = atomicAdd(&wf.counters[1], (uint32_t)__popc(mNext));
-      if(mSh) baseSh = atomicAdd(&wf.counters[2], (uint32_t)__popc(mSh));
+      if(mSh) baseSh = atomicAdd(&wf.counters[wf.shadowSlot ? 5 : 2], (uint32_t)__popc(mSh));
     }
     baseNext = __shfl_sync(0xffffffffu, baseNext, 0);
     baseSh   = __shfl_sync(0xffffffffu, baseSh, 0);
@@ -559,12 +561,21 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(cons
 __global__ void swapQueuesKernel(Wavefront wf, TraceStats* stats)
 {
   if(stats)
-    atomicAdd(&stats->shadowRays, (unsigned long long)wf.counters[2]);
+    atomicAdd(&stats->shadowRays, (unsigned long long)wf.counters[wf.shadowSlot ? 5 : 2]);
   wf.counters[0] = wf.counters[1];
   wf.counters[1] = 0;
-  wf.counters[2] = 0;
   wf.counters[3] = 0;
-  wf.counters[4] = 0;
+  // this bounce's shadow count/cursor may still be in use by its any-hit kernel: reset the pair of the next bounce
+  if(wf.shadowSlot)
+  {
+    wf.counters[2] = 0;
+    wf.counters[4] = 0;
+  }
+  else
+  {
+    wf.counters[5] = 0;
+    wf.counters[6] = 0;
+  }
 }
 
 // ---- sample finish: firefly clamp (pathtrace.glsl:380-384) + pixel sample sum (pathtrace.comp:102-105) ---

@@ -24,6 +24,7 @@
 #include "vkrt_device.cuh"
 #include "vkrt_texture.cuh"
 #include <cstdlib>
+#include <cstring>
 #include "vkrt_internal.h"
 
 namespace vkrt {
@@ -33,6 +34,12 @@ namespace vkrt {
 #endif
 #ifndef VKRT_REFETCH
 #define VKRT_REFETCH 24
+#endif
+#ifndef VKRT_TRACE_MINBLOCKS
+#define VKRT_TRACE_MINBLOCKS 8
+#endif
+#ifndef VKRT_WIDE_MINBLOCKS
+#define VKRT_WIDE_MINBLOCKS 8
 #endif
 #ifndef VKRT_TRACE_BLOCK
 #define VKRT_TRACE_BLOCK 128
@@ -84,12 +91,29 @@ VKRT_D void loadNode256(const float4* __restrict__ nodes, uint32_t node, float4&
       : "l"(p + 2));
 }
 
+// One 32-byte quantised node (quantizeBvh) as a single 256-bit load.
+VKRT_D void loadQNode(const uint4* __restrict__ qnodes, uint32_t node, uint32_t (&w)[8])
+{
+  const uint4* p = qnodes + 2ull * node;
+  asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+      : "l"(p));
+}
+// 2^23 + q as a float: the 16-bit grid coordinate dropped into the mantissa of 0x4B000000 by one byte permute;
+// sel = 0x7610 picks the low half-word (box min), 0x7632 the high one (box max)
+VKRT_D float gridPlane(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)); }
+
 VKRT_D float safeInv(float x) { return 1.0f / (fabsf(x) < 1e-20f ? copysignf(1e-20f, x) : x); }
 
-template <int MODE, bool COUNT, int VARIANT>
-__global__ void __launch_bounds__(kTraceBlock, 8) traceKernel(const __grid_constant__ SceneView sc, const __grid_constant__ TraceLaunch L)
+__device__ __noinline__ void stackSpill(uint32_t* l, int i, uint32_t v) { l[min(i, kStackLocal - 1)] = v; }
+__device__ __noinline__ uint32_t stackFill(const uint32_t* l, int i) { return l[min(i, kStackLocal - 1)]; }
+
+enum NodeFormat { FMT_LOHI = 0, FMT_Q32 = 1, FMT_CE = 2 };
+
+template <int MODE, bool COUNT, int VARIANT, int FMT>
+__global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel(const __grid_constant__ SceneView sc, const __grid_constant__ TraceLaunch L)
 {
-  __shared__ uint32_t s_stack[kStackShared * kTraceBlock];
+  __shared__ uint32_t s_stack[(kStackShared > 0 ? kStackShared : 1) * (kStackShared > 0 ? kTraceBlock : 1)];
   uint32_t* const sstack = &s_stack[threadIdx.x];
   uint32_t        lstack[kStackLocal];
   const uint32_t  n    = *L.count;
@@ -115,32 +139,41 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernel(const __grid_const
     return;
   }
 
-  const float4* __restrict__ nodes = sc.nodes;
-  const float4* __restrict__ tris  = sc.tris;
+  const float4* __restrict__ nodes  = sc.nodes;
+  const uint4* __restrict__  qnodes = sc.qnodes;
+  const float4* __restrict__ cnodes = sc.cnodes;
+  constexpr bool QN = (FMT == FMT_Q32);
+  const float4* __restrict__ tris   = sc.tris;
 
   // per-lane ray + traversal state (lives across refills)
   bool     haveRay = false;
-  uint32_t slot = 0, seed = 0;
+  uint32_t slot = 0;
   float3   o = f3(0.f), d = f3(0.f), id = f3(0.f);
-  float    tmax = 0.f, bestT = 0.f, bestU = 0.f, bestV = 0.f;
+  // QN: id is the inverse direction in grid units, nood = t0 - (o_g + 2^23) * id, selN/selF pick the near/far plane
+  float3   nood = f3(0.f);
+  uint32_t selNx = 0, selNy = 0, selNz = 0;
+  float    bestT = 0.f, bestU = 0.f, bestV = 0.f;
   uint32_t bestTri = ~0u;
   uint32_t node = kDone, leaf = 0;
   int      sp = 0;
   bool     exhausted = false;  // warp uniform: the queue has been handed out completely
   uint32_t nNodes = 0, nTris = 0;
 
+  // the overflow half of the stack sits behind real calls, so that the common path is one predicated shared-memory access
   auto push = [&](uint32_t v) {
     if(sp < kStackShared)
       sstack[sp * kTraceBlock] = v;
     else
-      lstack[min(sp - kStackShared, kStackLocal - 1)] = v;
+      stackSpill(lstack, sp - kStackShared, v);
     sp++;
   };
   auto pop = [&]() -> uint32_t {
     if(sp == 0)
       return kDone;
     --sp;
-    return sp < kStackShared ? sstack[sp * kTraceBlock] : lstack[min(sp - kStackShared, kStackLocal - 1)];
+    if(sp < kStackShared)
+      return sstack[sp * kTraceBlock];
+    return stackFill(lstack, sp - kStackShared);
   };
 
   for(;;)
@@ -163,11 +196,37 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernel(const __grid_const
           slot = (MODE != MODE_SHADOW_RESOLVE && L.queue) ? L.queue[i] : i;
           const float4 ro = L.rayO[slot], rd = L.rayD[slot];
           o = f3(ro); d = f3(rd);
-          tmax = ro.w; seed = __float_as_uint(rd.w);
-          id      = f3(safeInv(d.x), safeInv(d.y), safeInv(d.z));
+          const float tmax = ro.w;
           bestT   = tmax; bestU = 0.f; bestV = 0.f; bestTri = ~0u;
           node    = 0; leaf = 0; sp = 0;
           haveRay = true;
+          if(QN)
+          {
+            // the ray in grid space; its origin is moved to (just before) the entry into the grid cube so that
+            // o_g + 2^23 keeps whole-cell resolution however far away the ray starts.  Box times stay world times.
+            const float3 dg = d * sc.gridInv;
+            id              = f3(safeInv(dg.x), safeInv(dg.y), safeInv(dg.z));
+            float3      og  = (o - sc.gridOrigin) * sc.gridInv;
+            const float ax = (0.0f - og.x) * id.x, bx = (65535.0f - og.x) * id.x;
+            const float ay = (0.0f - og.y) * id.y, by = (65535.0f - og.y) * id.y;
+            const float az = (0.0f - og.z) * id.z, bz = (65535.0f - og.z) * id.z;
+            const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+            const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+            if(!(tn <= tf * 1.0002f))
+              node = kDone;  // misses the whole scene
+            const float t0 = tn * 0.99995f;
+            og             = og + dg * t0;
+            nood  = f3(t0 - (og.x + 8388608.0f) * id.x, t0 - (og.y + 8388608.0f) * id.y, t0 - (og.z + 8388608.0f) * id.z);
+            selNx = (__float_as_uint(id.x) >> 31) ? 0x7632u : 0x7610u;
+            selNy = (__float_as_uint(id.y) >> 31) ? 0x7632u : 0x7610u;
+            selNz = (__float_as_uint(id.z) >> 31) ? 0x7632u : 0x7610u;
+          }
+          else
+          {
+            id = f3(safeInv(d.x), safeInv(d.y), safeInv(d.z));
+            if(FMT == FMT_CE)
+              nood = f3(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
+          }
         }
       }
       exhausted = (base + want >= n);
@@ -182,22 +241,67 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernel(const __grid_const
         // ---- inner nodes, until every lane of the warp has parked a leaf ---------------------
         while(node < kDone)  // inner index (leaf codes have bit 31 set, kDone is larger than any index)
         {
+          float    tn0, tf0, tn1, tf1;
+          uint32_t c0, c1;
+          if(COUNT) nNodes++;
+          if(QN)
+          {
+            uint32_t w[8];
+            loadQNode(qnodes, node, w);
+            // far selectors are re-derived per node (volatile: keeps them out of registers that would otherwise spill)
+            uint32_t selFx, selFy, selFz;
+            asm volatile("xor.b32 %0, %1, 0x22;" : "=r"(selFx) : "r"(selNx));
+            asm volatile("xor.b32 %0, %1, 0x22;" : "=r"(selFy) : "r"(selNy));
+            asm volatile("xor.b32 %0, %1, 0x22;" : "=r"(selFz) : "r"(selNz));
+            tn0 = fmaxf(fmaxf(__fmaf_rn(gridPlane(w[0], selNx), id.x, nood.x), __fmaf_rn(gridPlane(w[1], selNy), id.y, nood.y)),
+                        fmaxf(__fmaf_rn(gridPlane(w[2], selNz), id.z, nood.z), 0.0f));
+            tf0 = fminf(fminf(__fmaf_rn(gridPlane(w[0], selFx), id.x, nood.x), __fmaf_rn(gridPlane(w[1], selFy), id.y, nood.y)),
+                        fminf(__fmaf_rn(gridPlane(w[2], selFz), id.z, nood.z), bestT));
+            tn1 = fmaxf(fmaxf(__fmaf_rn(gridPlane(w[3], selNx), id.x, nood.x), __fmaf_rn(gridPlane(w[4], selNy), id.y, nood.y)),
+                        fmaxf(__fmaf_rn(gridPlane(w[5], selNz), id.z, nood.z), 0.0f));
+            tf1 = fminf(fminf(__fmaf_rn(gridPlane(w[3], selFx), id.x, nood.x), __fmaf_rn(gridPlane(w[4], selFy), id.y, nood.y)),
+                        fminf(__fmaf_rn(gridPlane(w[5], selFz), id.z, nood.z), bestT));
+            c0 = w[6];
+            c1 = w[7];
+          }
+          else if(FMT == FMT_CE)
+          {
+            // centre / half-extent boxes (centerNodesKernel): everything up to the 3-input min/max runs on the FMA pipe
+            float4 m0, m1, m2, m3;
+            loadNode256(cnodes, node, m0, m1, m2, m3);
+            const float c0x = __fmaf_rn(m0.x, id.x, nood.x), c0y = __fmaf_rn(m0.z, id.y, nood.y), c0z = __fmaf_rn(m2.x, id.z, nood.z);
+            const float c1x = __fmaf_rn(m1.x, id.x, nood.x), c1y = __fmaf_rn(m1.z, id.y, nood.y), c1z = __fmaf_rn(m2.z, id.z, nood.z);
+            const float aix = fabsf(id.x), aiy = fabsf(id.y), aiz = fabsf(id.z);
+            tn0 = fmaxf(fmaxf(__fmaf_rn(-m0.y, aix, c0x), __fmaf_rn(-m0.w, aiy, c0y)), __fmaf_rn(-m2.y, aiz, c0z));
+            tf0 = fminf(fminf(__fmaf_rn(m0.y, aix, c0x), __fmaf_rn(m0.w, aiy, c0y)), __fmaf_rn(m2.y, aiz, c0z));
+            tn1 = fmaxf(fmaxf(__fmaf_rn(-m1.y, aix, c1x), __fmaf_rn(-m1.w, aiy, c1y)), __fmaf_rn(-m2.w, aiz, c1z));
+            tf1 = fminf(fminf(__fmaf_rn(m1.y, aix, c1x), __fmaf_rn(m1.w, aiy, c1y)), __fmaf_rn(m2.w, aiz, c1z));
+            tf0 = fminf(tf0, bestT);
+            tf1 = fminf(tf1, bestT);
+            c0  = __float_as_uint(m3.x);
+            c1  = __float_as_uint(m3.y);
+          }
+          else
+          {
           float4 n0, n1, n2, n3;
           loadNode256(nodes, node, n0, n1, n2, n3);
-          if(COUNT) nNodes++;
           const float a0x = (n0.x - o.x) * id.x, b0x = (n0.y - o.x) * id.x;
           const float a0y = (n0.z - o.y) * id.y, b0y = (n0.w - o.y) * id.y;
           const float a0z = (n2.x - o.z) * id.z, b0z = (n2.y - o.z) * id.z;
           const float a1x = (n1.x - o.x) * id.x, b1x = (n1.y - o.x) * id.x;
           const float a1y = (n1.z - o.y) * id.y, b1y = (n1.w - o.y) * id.y;
           const float a1z = (n2.z - o.z) * id.z, b1z = (n2.w - o.z) * id.z;
-          const float tn0 = fmaxf(fmaxf(fminf(a0x, b0x), fminf(a0y, b0y)), fmaxf(fminf(a0z, b0z), 0.0f));
-          const float tf0 = fminf(fminf(fmaxf(a0x, b0x), fmaxf(a0y, b0y)), fminf(fmaxf(a0z, b0z), bestT));
-          const float tn1 = fmaxf(fmaxf(fminf(a1x, b1x), fminf(a1y, b1y)), fmaxf(fminf(a1z, b1z), 0.0f));
-          const float tf1 = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fminf(fmaxf(a1z, b1z), bestT));
-          const bool  h0  = tn0 <= tf0 * 1.0002f;  // conservative: never reject a box the triangle test could hit
-          const bool  h1  = tn1 <= tf1 * 1.0002f;
-          uint32_t    c0 = __float_as_uint(n3.x), c1 = __float_as_uint(n3.y);
+          tn0 = fmaxf(fmaxf(fminf(a0x, b0x), fminf(a0y, b0y)), fmaxf(fminf(a0z, b0z), 0.0f));
+          tf0 = fminf(fminf(fmaxf(a0x, b0x), fmaxf(a0y, b0y)), fminf(fmaxf(a0z, b0z), bestT));
+          tn1 = fmaxf(fmaxf(fminf(a1x, b1x), fminf(a1y, b1y)), fmaxf(fminf(a1z, b1z), 0.0f));
+          tf1 = fminf(fminf(fmaxf(a1x, b1x), fmaxf(a1y, b1y)), fminf(fmaxf(a1z, b1z), bestT));
+          c0  = __float_as_uint(n3.x);
+          c1  = __float_as_uint(n3.y);
+          }
+          // conservative: never reject a box the triangle test could hit.  FMT_CE leaves tn unclamped: max(tn,0) <= x is tn <= x && 0 <= x
+          const float x0 = tf0 * 1.0002f, x1 = tf1 * 1.0002f;
+          const bool  h0 = (FMT == FMT_CE) ? (tn0 <= x0 && x0 >= 0.0f) : (tn0 <= x0);
+          const bool  h1 = (FMT == FMT_CE) ? (tn1 <= x1 && x1 >= 0.0f) : (tn1 <= x1);
           if(h0 && h1)
           {
             if(tn1 < tn0)
@@ -274,11 +378,10 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernel(const __grid_const
             if(!(v >= 0.0f && (u + v) <= 1.0f))
               continue;
             const float t = dot(e2, q) * inv;
-            if(!(t > 0.0f && t < tmax))
+            // t in (0, tmax): bestT starts at tmax, so only the tie branch has to exclude "no hit yet"
+            if(!(t > 0.0f && (t < bestT || (t == bestT && bestTri != ~0u && triId < bestTri))))
               continue;
-            if(!(t < bestT || (t == bestT && triId < bestTri)))
-              continue;
-            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, u, v, seed))
+            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, u, v, __float_as_uint(L.rayD[slot].w)))
               continue;
             bestT = t; bestU = u; bestV = v; bestTri = triId;
             if(MODE != MODE_CLOSEST)
@@ -340,10 +443,273 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernel(const __grid_const
 }
 
 
+// ---------------------------------------------------------------------------------------------
+// BVH4 traversal (collapseBvhWide): same persistent while-while structure, same triangle test, same results.
+// One step = two 256-bit loads + four grid-space slab tests; the nearest hit child is entered, the others are pushed.
+constexpr uint32_t kEmptyRef = 0xffffffffu;
+
+template <int MODE, bool COUNT>
+__global__ void __launch_bounds__(kTraceBlock, VKRT_WIDE_MINBLOCKS) traceKernelWide(const __grid_constant__ SceneView sc, const __grid_constant__ TraceLaunch L)
+{
+  __shared__ uint32_t s_stack[(kStackShared > 0 ? kStackShared : 1) * (kStackShared > 0 ? kTraceBlock : 1)];
+  uint32_t* const sstack = &s_stack[threadIdx.x];
+  uint32_t        lstack[kStackLocal];
+  const uint32_t  n    = *L.count;
+  const uint32_t  lane = threadIdx.x & 31u;
+
+  if(sc.numTris == 0)
+  {
+    for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+      const uint32_t slot = (MODE != MODE_SHADOW_RESOLVE && L.queue) ? L.queue[i] : i;
+      if(MODE == MODE_SHADOW_RESOLVE)
+      {
+        const float4 c = L.shC[i];
+        float4       r = L.rad[__float_as_uint(c.w)];
+        r.x += c.x; r.y += c.y; r.z += c.z;
+        L.rad[__float_as_uint(c.w)] = r;
+      }
+      else
+        L.hit[slot] = f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u));
+    }
+    return;
+  }
+
+  const uint4* __restrict__  wnodes = sc.wnodes;
+  const float4* __restrict__ tris   = sc.tris;
+
+  bool     haveRay = false;
+  uint32_t slot = 0;
+  float3   o = f3(0.f), d = f3(0.f), id = f3(0.f), nood = f3(0.f);
+  uint32_t selNx = 0, selNy = 0, selNz = 0;
+  float    bestT = 0.f, bestU = 0.f, bestV = 0.f;
+  uint32_t bestTri = ~0u;
+  uint32_t node = kDone, leaf = 0;
+  int      sp = 0;
+  bool     exhausted = false;
+  uint32_t nNodes = 0, nTris = 0;
+
+  // the overflow half of the stack sits behind real calls, so that the common path is one predicated shared-memory access
+  auto push = [&](uint32_t v) {
+    if(sp < kStackShared)
+      sstack[sp * kTraceBlock] = v;
+    else
+      stackSpill(lstack, sp - kStackShared, v);
+    sp++;
+  };
+  auto pop = [&]() -> uint32_t {
+    if(sp == 0)
+      return kDone;
+    --sp;
+    if(sp < kStackShared)
+      return sstack[sp * kTraceBlock];
+    return stackFill(lstack, sp - kStackShared);
+  };
+
+  for(;;)
+  {
+    __syncwarp();
+    const unsigned idle = __ballot_sync(kFull, !haveRay);
+    if(idle && !exhausted)
+    {
+      const uint32_t want = (uint32_t)__popc(idle);
+      uint32_t       base = 0;
+      if(lane == 0)
+        base = atomicAdd(L.cursor, want);
+      base = __shfl_sync(kFull, base, 0);
+      if(!haveRay)
+      {
+        const uint32_t i = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+        if(i < n)
+        {
+          slot = (MODE != MODE_SHADOW_RESOLVE && L.queue) ? L.queue[i] : i;
+          const float4 ro = L.rayO[slot], rd = L.rayD[slot];
+          o = f3(ro); d = f3(rd);
+          const float tmax = ro.w;
+          bestT   = tmax; bestU = 0.f; bestV = 0.f; bestTri = ~0u;
+          node    = 0; leaf = 0; sp = 0;
+          haveRay = true;
+          // grid-space ray, see traceKernel<QN>
+          const float3 dg = d * sc.gridInv;
+          id              = f3(safeInv(dg.x), safeInv(dg.y), safeInv(dg.z));
+          float3      og  = (o - sc.gridOrigin) * sc.gridInv;
+          const float ax = (0.0f - og.x) * id.x, bx = (65535.0f - og.x) * id.x;
+          const float ay = (0.0f - og.y) * id.y, by = (65535.0f - og.y) * id.y;
+          const float az = (0.0f - og.z) * id.z, bz = (65535.0f - og.z) * id.z;
+          const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+          const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+          if(!(tn <= tf * 1.0002f))
+            node = kDone;
+          const float t0 = tn * 0.99995f;
+          og             = og + dg * t0;
+          nood  = f3(t0 - (og.x + 8388608.0f) * id.x, t0 - (og.y + 8388608.0f) * id.y, t0 - (og.z + 8388608.0f) * id.z);
+          selNx = (__float_as_uint(id.x) >> 31) ? 0x7632u : 0x7610u;
+          selNy = (__float_as_uint(id.y) >> 31) ? 0x7632u : 0x7610u;
+          selNz = (__float_as_uint(id.z) >> 31) ? 0x7632u : 0x7610u;
+        }
+      }
+      exhausted = (base + want >= n);
+    }
+    if(!__any_sync(kFull, haveRay))
+      break;
+
+    if(haveRay)
+    {
+      while(node != kDone || leaf != 0)
+      {
+        while(node < kDone)
+        {
+          uint32_t w[16];
+          {
+            const uint4* p = wnodes + 4ull * node;
+            asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                : "l"(p));
+            asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15])
+                : "l"(p + 2));
+          }
+          if(COUNT) nNodes++;
+          const uint32_t selFx = selNx ^ 0x0022u, selFy = selNy ^ 0x0022u, selFz = selNz ^ 0x0022u;
+          float    nearT = kInfinity;
+          uint32_t nearRef = kDone;
+          bool     h[4];
+          float    tn[4];
+#pragma unroll
+          for(int k = 0; k < 4; k++)
+          {
+            const float a = fmaxf(fmaxf(__fmaf_rn(gridPlane(w[3 * k + 0], selNx), id.x, nood.x), __fmaf_rn(gridPlane(w[3 * k + 1], selNy), id.y, nood.y)),
+                                  fmaxf(__fmaf_rn(gridPlane(w[3 * k + 2], selNz), id.z, nood.z), 0.0f));
+            const float b = fminf(fminf(__fmaf_rn(gridPlane(w[3 * k + 0], selFx), id.x, nood.x), __fmaf_rn(gridPlane(w[3 * k + 1], selFy), id.y, nood.y)),
+                                  fminf(__fmaf_rn(gridPlane(w[3 * k + 2], selFz), id.z, nood.z), bestT));
+            h[k]  = (a <= b * 1.0002f) && (w[12 + k] != kEmptyRef);
+            tn[k] = a;
+            if(h[k] && a < nearT)
+            {
+              nearT   = a;
+              nearRef = w[12 + k];
+            }
+          }
+          if(nearRef != kDone)
+          {
+            // enter the nearest child; the other hit children wait on the stack
+#pragma unroll
+            for(int k = 0; k < 4; k++)
+              if(h[k] && w[12 + k] != nearRef)
+                push(w[12 + k]);
+            node = nearRef;
+          }
+          else
+            node = pop();
+          if((node & kLeafBit) && leaf == 0)
+          {
+            leaf = node;
+            node = pop();
+          }
+          if(__popc(__ballot_sync(__activemask(), leaf == 0)) <= 8)
+            break;
+        }
+
+        while(leaf != 0)
+        {
+          const uint32_t first = leaf & kLeafMask;
+          const uint32_t cnt   = ((leaf >> kLeafCntSh) & 7u) + 1u;
+          for(uint32_t k = 0; k < cnt; k++)
+          {
+            const float4 q0 = __ldg(&tris[3ull * (first + k) + 0]);
+            const float4 q1 = __ldg(&tris[3ull * (first + k) + 1]);
+            const float4 q2 = __ldg(&tris[3ull * (first + k) + 2]);
+            if(COUNT) nTris++;
+            const uint32_t flags = __float_as_uint(q0.w);
+            const uint32_t triId = __float_as_uint(q1.w);
+            const float3 v0  = f3(q0);
+            const float3 e1  = f3(q1) - v0;
+            const float3 e2  = f3(q2) - v0;
+            const float3 p   = cross(d, e2);
+            const float  det = dot(e1, p);
+            if(!(flags & TRI_CULL_DISABLE))
+            {
+              const bool front = (flags & TRI_FLIP_FACING) ? (det < 0.0f) : (det > 0.0f);
+              if(!front)
+                continue;
+            }
+            if(det == 0.0f || !(det == det))
+              continue;
+            const float  inv = 1.0f / det;
+            const float3 tv  = o - v0;
+            const float  u   = dot(tv, p) * inv;
+            if(!(u >= 0.0f && u <= 1.0f))
+              continue;
+            const float3 q = cross(tv, e1);
+            const float  v = dot(d, q) * inv;
+            if(!(v >= 0.0f && (u + v) <= 1.0f))
+              continue;
+            const float t = dot(e2, q) * inv;
+            if(!(t > 0.0f && (t < bestT || (t == bestT && bestTri != ~0u && triId < bestTri))))
+              continue;
+            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, u, v, __float_as_uint(L.rayD[slot].w)))
+              continue;
+            bestT = t; bestU = u; bestV = v; bestTri = triId;
+            if(MODE != MODE_CLOSEST)
+            {
+              node = kDone;
+              sp   = 0;
+              break;
+            }
+          }
+          if(node & kLeafBit)
+          {
+            leaf = node;
+            node = pop();
+          }
+          else
+            leaf = 0;
+          if(MODE != MODE_CLOSEST && bestTri != ~0u)
+          {
+            leaf = 0;
+            node = kDone;
+          }
+        }
+
+        if(!exhausted && __popc(__activemask()) < kRefetchThreshold)
+          break;
+      }
+
+      if(node == kDone && leaf == 0)
+      {
+        if(MODE == MODE_CLOSEST)
+          L.hit[slot] = (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(bestT, bestU, bestV, __uint_as_float(bestTri));
+        else if(MODE == MODE_ANY_PROBE)
+          L.hit[slot] = (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(0.f, 0.f, 0.f, __uint_as_float(0u));
+        else if(bestTri == ~0u)
+        {
+          const float4   c    = L.shC[slot];
+          const uint32_t path = __float_as_uint(c.w);
+          float4         rad  = L.rad[path];
+          rad.x += c.x; rad.y += c.y; rad.z += c.z;
+          L.rad[path] = rad;
+        }
+        haveRay = false;
+      }
+    }
+  }
+
+  if(COUNT && L.stats)
+  {
+    atomicAdd(&L.stats->nodesVisited, (unsigned long long)nNodes);
+    atomicAdd(&L.stats->trisTested, (unsigned long long)nTris);
+    if(MODE == MODE_SHADOW_RESOLVE)
+    {
+      atomicAdd(&L.stats->shadowNodes, (unsigned long long)nNodes);
+      atomicAdd(&L.stats->shadowTris, (unsigned long long)nTris);
+    }
+  }
+}
+
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, 8) traceKernelIfIf(const __grid_constant__ SceneView sc, const __grid_constant__ TraceLaunch L)
 {
-  __shared__ uint32_t s_stack[kStackShared * kTraceBlock];
+  __shared__ uint32_t s_stack[(kStackShared > 0 ? kStackShared : 1) * (kStackShared > 0 ? kTraceBlock : 1)];
   uint32_t* const sstack = &s_stack[threadIdx.x];
   uint32_t        lstack[kStackLocal];
   const uint32_t  n    = *L.count;
@@ -584,7 +950,7 @@ struct WarpShared
 template <int MODE, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, 8) traceKernelCoop(const __grid_constant__ SceneView sc, const __grid_constant__ TraceLaunch L)
 {
-  __shared__ uint32_t   s_stack[kStackShared * kTraceBlock];
+  __shared__ uint32_t   s_stack[(kStackShared > 0 ? kStackShared : 1) * kTraceBlock];
   __shared__ WarpShared s_ws[kTraceBlock / 32];
   uint32_t* const sstack = &s_stack[threadIdx.x];
   WarpShared&     ws     = s_ws[threadIdx.x >> 5];
@@ -892,21 +1258,67 @@ static void launchTraceIfIf(cudaStream_t s, const SceneView& scene, const TraceL
   traceKernelIfIf<MODE, COUNT><<<grid, kTraceBlock, 0, s>>>(scene, L);
 }
 
-template <int MODE, bool COUNT, int VARIANT>
+template <int MODE, bool COUNT, int VARIANT, int FMT>
 static void launchTraceV(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, int numSMs)
 {
   static int grid = 0;
   if(!grid)
   {
     int perSM = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernel<MODE, COUNT, VARIANT>, kTraceBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernel<MODE, COUNT, VARIANT, FMT>, kTraceBlock, 0);
     grid = numSMs * (perSM < 1 ? 1 : perSM);
   }
-  traceKernel<MODE, COUNT, VARIANT><<<grid, kTraceBlock, 0, s>>>(scene, L);
+  traceKernel<MODE, COUNT, VARIANT, FMT><<<grid, kTraceBlock, 0, s>>>(scene, L);
+}
+// Node format read by the default traversal kernel (VKRT_NODE_FORMAT): "ce" centre / half-extent fp32 (default, 64 bytes),
+// "lohi" min / max fp32 (64 bytes), "q32" 16-bit grid boxes (32 bytes).  The experimental loop variants only exist for "lohi".
+int traceNodeFormat()
+{
+  static int fmt = -1;
+  if(fmt < 0)
+  {
+    const char* e = getenv("VKRT_NODE_FORMAT");
+    const char* v = getenv("VKRT_TRACE_VARIANT");
+    fmt           = FMT_CE;
+    if(e && !strcmp(e, "lohi")) fmt = FMT_LOHI;
+    if(e && !strcmp(e, "q32")) fmt = FMT_Q32;
+    if(v && atoi(v) != 8) fmt = FMT_LOHI;
+  }
+  return fmt;
+}
+int traceNodeBytes() { return (traceBvhWidth() == 4) ? 64 : (traceNodeFormat() == FMT_Q32 ? 32 : 64); }
+template <int MODE, bool COUNT>
+static void launchTraceWide(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, int numSMs)
+{
+  static int grid = 0;
+  if(!grid)
+  {
+    int perSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, traceKernelWide<MODE, COUNT>, kTraceBlock, 0);
+    grid = numSMs * (perSM < 1 ? 1 : perSM);
+  }
+  traceKernelWide<MODE, COUNT><<<grid, kTraceBlock, 0, s>>>(scene, L);
+}
+// Tree width of the active traversal kernel: 2 (binary, default) or 4 via VKRT_BVH_WIDTH.
+int traceBvhWidth()
+{
+  static int width = 0;
+  if(!width)
+  {
+    const char* e = getenv("VKRT_BVH_WIDTH");
+    const char* v = getenv("VKRT_TRACE_VARIANT");
+    width         = (e && atoi(e) == 4 && !(v && atoi(v) != 8)) ? 4 : 2;
+  }
+  return width;
 }
 template <int MODE, bool COUNT>
 static void launchTrace(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, int numSMs)
 {
+  if(traceBvhWidth() == 4)
+  {
+    launchTraceWide<MODE, COUNT>(s, scene, L, numSMs);
+    return;
+  }
   static int variant = -1;
   if(variant < 0)
   {
@@ -917,11 +1329,18 @@ static void launchTrace(cudaStream_t s, const SceneView& scene, const TraceLaunc
   {
     case 100: launchTraceCoop<MODE, COUNT>(s, scene, L, numSMs); break;
     case 200: launchTraceIfIf<MODE, COUNT>(s, scene, L, numSMs); break;
-    case 1: launchTraceV<MODE, COUNT, 1>(s, scene, L, numSMs); break;
-    case 4: launchTraceV<MODE, COUNT, 4>(s, scene, L, numSMs); break;
-    case 8: launchTraceV<MODE, COUNT, 8>(s, scene, L, numSMs); break;
-    case 16: launchTraceV<MODE, COUNT, 16>(s, scene, L, numSMs); break;
-    default: launchTraceV<MODE, COUNT, 0>(s, scene, L, numSMs); break;
+    case 1: launchTraceV<MODE, COUNT, 1, FMT_LOHI>(s, scene, L, numSMs); break;
+    case 4: launchTraceV<MODE, COUNT, 4, FMT_LOHI>(s, scene, L, numSMs); break;
+    case 8:
+      if(traceNodeFormat() == FMT_Q32)
+        launchTraceV<MODE, COUNT, 8, FMT_Q32>(s, scene, L, numSMs);
+      else if(traceNodeFormat() == FMT_CE)
+        launchTraceV<MODE, COUNT, 8, FMT_CE>(s, scene, L, numSMs);
+      else
+        launchTraceV<MODE, COUNT, 8, FMT_LOHI>(s, scene, L, numSMs);
+      break;
+    case 16: launchTraceV<MODE, COUNT, 16, FMT_LOHI>(s, scene, L, numSMs); break;
+    default: launchTraceV<MODE, COUNT, 0, FMT_LOHI>(s, scene, L, numSMs); break;
   }
 }
 
