@@ -54,7 +54,10 @@ typedef struct vkrt_render_opts
   int32_t count_traversal;  /* 1 = run the instrumented traversal kernels (visit counters) */
   int32_t sort_rays;        /* 1 = sort the ray queue by direction octant / origin Morton key */
   int32_t profile;          /* 1 = time every kernel family with CUDA events (vkrt_stats.ms_*) */
-  int32_t reserved[8];
+  int32_t precise_shading;  /* 0 (default): the shade kernel uses approximate division / sqrt and SFU sin/cos/exp/log/pow, as a GLSL
+                               compiler does; 1: IEEE-exact arithmetic throughout (what the oracle comparisons at 1e-4 use).
+                               Ray generation, traversal and intersection are exact in both. */
+  int32_t reserved[7];
 } vkrt_render_opts;
 
 typedef struct vkrt_stats

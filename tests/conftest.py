@@ -41,6 +41,9 @@ def vk(built):
 @pytest.fixture(scope="session")
 def gpu(vk):
     ctx = vk.Context(0)
+    # oracle comparisons use the IEEE-exact shade kernel (vkrt_render_opts.precise_shading = 1); the default fast shade
+    # kernel has its own tests (test_fast_shading_*) and is what the full-size property tests and bench.py run
+    ctx.precise_default = True
     yield ctx
     ctx.close()
 

@@ -294,6 +294,41 @@ def test_full_size_properties_sponza_1080p(vk, gpu, build_mode):
     assert off.mean() < 0.002 and per_channel_rel_l2(got[~off], ref[~off]) < IMG_TOL
 
 
+@pytest.mark.parametrize("pbr", [0, 1])
+def test_fast_shading_against_precise_and_oracle(vk, ob, gpu, pbr):
+    """The default shade kernel (approximate division / sqrt, SFU sin/cos/exp/log/pow -- what a GLSL compiler emits too) against
+    the IEEE-exact one and the oracle.  Primary rays and traversal are exact in both, so frame-0 geometry is identical; radiance
+    differs by rounding, and a small fraction of multi-bounce paths takes another branch (chaotic in glossy scenes)."""
+    from vk_raytrace_b200 import scenes, structs as S
+    for sc, W, H, depth, max_off in ((scenes.cornell_box(with_light=True), 64, 64, 4, 0.002), (small_sponza(), 96, 64, 6, 0.02)):
+        o = both(vk, ob, gpu, sc, W, H)
+        st = S.default_rtx_state(W, H, maxDepth=depth, pbrMode=pbr)
+        gpu.render(st, 4, precise=True)
+        exact = gpu.output_read()[..., :3]
+        gpu.output_clear()
+        gpu.render(st, 4, precise=False)
+        fast = gpu.output_read()[..., :3]
+        gpu.output_clear()
+        gpu.render(st, 4, precise=False)
+        assert np.array_equal(fast, gpu.output_read()[..., :3]) and np.isfinite(fast).all()      # deterministic
+        o.render(st, 4)
+        ref = o.output_read()[..., :3]
+        for other in (exact, ref):
+            off = (np.abs(fast - other) > 1e-3 * (1 + np.abs(other))).any(axis=2)
+            assert off.mean() <= max_off, off.mean()
+            assert per_channel_rel_l2(fast[~off], other[~off]) < 1e-3        # north_star tolerance
+        # debug views that do not depend on the path history are identical or within rounding
+        for dbg in (1, 2, 5, 7):   # base colour, normal, alpha, texcoord (shaders/host_device.h:88-102)
+            sd = S.default_rtx_state(W, H, maxDepth=depth, pbrMode=pbr, debugging_mode=dbg)
+            imgs = []
+            for precise in (True, False):
+                gpu.output_clear()
+                gpu.render(sd, 1, precise=precise)
+                imgs.append(gpu.output_read()[..., :3])
+            bad = (np.abs(imgs[0] - imgs[1]) > 1e-4).any(axis=2)
+            assert bad.mean() <= 0.002, (dbg, bad.mean())
+
+
 def test_cpp_renderer_adaptor_headless(vk):
     """`CudaRenderer : Renderer` (vk_raytrace_b200/host/) driven like src/main.cpp drives a back-end."""
     import subprocess
@@ -330,7 +365,8 @@ def test_gltf_file_to_image_end_to_end(vk, ob, tmp_path, pbr):
     # 0.02-0.05: D ~ 1/alpha^4) amplify it to percent-level differences in a percent of the pixels -- the same spread two
     # runs of the reference with a nudged camera would show -- so the deep comparison is statistical.
     for frames, depth, max_off, tol in ((4, 1, 0.0005, 1e-4), (4, 5, 0.03, 2e-3)):
-        out = subprocess.run([exe, gltf, env, str(W), str(H), str(frames), str(depth), str(tmp_path / "o"), str(pbr)], capture_output=True, text=True, timeout=300)
+        out = subprocess.run([exe, gltf, env, str(W), str(H), str(frames), str(depth), str(tmp_path / "o"), str(pbr)], capture_output=True, text=True, timeout=300,
+                             env=dict(os.environ, VKRT_SHADING="precise"))   # the oracle comparison below is for the IEEE-exact shade kernel
         assert out.returncode == 0, out.stderr + out.stdout
         got = np.fromfile(str(tmp_path / "o.f32"), dtype=np.float32).reshape(H, W, 4)[..., :3]
         st = S.default_rtx_state(W, H, maxDepth=depth, pbrMode=pbr, fireflyClampThreshold=integral * 4.0)

@@ -191,7 +191,17 @@ class Context:
         return out
 
     # ---- render ----
-    def render(self, state, num_frames=1, opts=None, sync=True):
+    def render(self, state, num_frames=1, opts=None, sync=True, precise=None):
+        """vkrt_render.  `precise` (or the context attribute `precise_default`) selects IEEE-exact shading arithmetic
+        (vkrt_render_opts.precise_shading = 1); the library default is the fast shade kernel."""
+        if precise is None:
+            precise = getattr(self, "precise_default", False)
+        if precise and (opts is None or not opts.precise_shading):
+            o = S.RenderOpts()
+            if opts is not None:
+                C.memmove(C.byref(o), C.byref(opts), C.sizeof(o))
+            o.precise_shading = 1
+            opts = o
         self._ck(self.lib.vkrt_render(self.h, C.byref(state), num_frames, None if opts is None else C.byref(opts)), "render")
         if sync:
             self.sync()

@@ -788,6 +788,9 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
   // per-kernel timing needs the kernels one after the other; otherwise shadow(b) overlaps closest(b+1) on a second stream
   static const bool overlapEnv = []() { const char* e = getenv("VKRT_OVERLAP"); return !e || atoi(e) != 0; }();
   const bool overlap  = overlapEnv && !timing;
+  // VKRT_SHADING=precise forces the IEEE-exact shade kernel for callers that cannot pass options (the C++ tools in tests)
+  static const bool envPrecise = []() { const char* e = getenv("VKRT_SHADING"); return e && !strcmp(e, "precise"); }();
+  if(envPrecise) o.precise_shading = 1;
   if(rank < 0 || rank >= shards)
     return fail(ctx, VKRT_ERR_INVALID, "render: shard_rank out of range");
 
@@ -840,7 +843,10 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
           cudaStreamWaitEvent(ctx->stream, ctx->evShadow, 0);  // shade(b) adds to the radiance shadow(b-1) resolves into
         {
           ScopedTimer t(ctx, timing, T_SHADE);
-          launchShade(ctx->stream, ctx->view, wf, fp, dstats, ctx->numSMs);
+          if(o.precise_shading)
+            launchShadePrecise(ctx->stream, ctx->view, wf, fp, dstats, ctx->numSMs);
+          else
+            launchShadeFast(ctx->stream, ctx->view, wf, fp, dstats, ctx->numSMs);
         }
         TraceLaunch S{};
         S.rayO = wf.shO; S.rayD = wf.shD; S.queue = nullptr;

@@ -71,7 +71,9 @@ struct FrameParams
   int32_t  depth;
 };
 void launchRaygen(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, int numSMs);
-void launchShade(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs);
+// vkrt_shade.cu is compiled twice: IEEE-exact arithmetic, and approximate division / sqrt / SFU transcendentals (the default)
+void launchShadePrecise(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs);
+void launchShadeFast(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs);
 void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, int numSMs);
 void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, int numSMs);
 void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats);

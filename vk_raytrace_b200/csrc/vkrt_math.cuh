@@ -52,7 +52,7 @@ VKRT_HD float  dot(float2 a, float2 b) { return a.x * b.x + a.y * b.y; }
 VKRT_HD float3 cross(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 VKRT_HD float  length(float3 a) { return sqrtf(dot(a, a)); }
 #if defined(__CUDA_ARCH__) && defined(VKRT_COMPACT_MATH)
-__device__ __noinline__ float3 normalize(float3 a)
+static __device__ __noinline__ float3 normalize(float3 a)
 #else
 VKRT_HD float3 normalize(float3 a)
 #endif
@@ -73,15 +73,25 @@ VKRT_HD float  smoothstepf(float e0, float e1, float x)
 // Payne-Hanek slow path), and the shade kernel uses dozens of them -- inlining every one blew the kernel up to
 // 16k instructions and made it instruction-fetch bound (profiles/README.md).  Results are unchanged.
 #if defined(__CUDA_ARCH__) && defined(VKRT_COMPACT_MATH)
-#define VKRT_MATHFN __device__ __noinline__
+#define VKRT_MATHFN static __device__ __noinline__
 #else
 #define VKRT_MATHFN VKRT_HD
 #endif
+#if defined(__CUDA_ARCH__) && defined(VKRT_FAST_MATH)
+// shading only (vkrt_shade.cu): SFU versions, a few ulp from libm -- the same order as the libm-vs-GLSL differences the
+// image tolerances already allow for; traversal and intersection never use these
+VKRT_HD float m_sinf(float x) { return __sinf(x); }
+VKRT_HD float m_cosf(float x) { return __cosf(x); }
+VKRT_HD float m_powf(float x, float y) { return __powf(x, y); }
+VKRT_HD float m_expf(float x) { return __expf(x); }
+VKRT_HD float m_logf(float x) { return __logf(x); }
+#else
 VKRT_MATHFN float m_sinf(float x) { return sinf(x); }
 VKRT_MATHFN float m_cosf(float x) { return cosf(x); }
 VKRT_MATHFN float m_powf(float x, float y) { return powf(x, y); }
 VKRT_MATHFN float m_expf(float x) { return expf(x); }
 VKRT_MATHFN float m_logf(float x) { return logf(x); }
+#endif
 VKRT_MATHFN float m_acosf(float x) { return acosf(x); }
 VKRT_MATHFN float m_asinf(float x) { return asinf(x); }
 VKRT_MATHFN float m_atan2f(float y, float x) { return atan2f(y, x); }
@@ -190,7 +200,7 @@ VKRT_HD float short_to_floatm11(int v)
   return (v >= 0) ? (u2f(0x3F800000u | (uint32_t(v) << 8)) - 1.0f) : (u2f(0xBF800000u | (uint32_t(-v) << 8)) + 1.0f);
 }
 #if defined(__CUDA_ARCH__) && defined(VKRT_COMPACT_MATH)
-__device__ __noinline__ float3 decompress_unit_vec(uint32_t packed)
+static __device__ __noinline__ float3 decompress_unit_vec(uint32_t packed)
 #else
 VKRT_HD float3 decompress_unit_vec(uint32_t packed)
 #endif

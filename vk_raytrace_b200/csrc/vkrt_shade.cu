@@ -26,6 +26,9 @@ namespace vkrt {
 constexpr int kShadeBlock     = VKRT_SHADE_BLOCK;
 constexpr int kShadeMinBlocks = VKRT_SHADE_MINBLOCKS;  // <= 96 registers: 640 threads per SM; large CTAs so that the phase barriers keep many warps in step
 
+// This file is compiled twice (Makefile): IEEE-exact (everything) and with VKRT_FAST_MATH (the shade kernel only, approximate
+// division / square root / SFU transcendentals).  Kernels that exist once live behind !VKRT_FAST_MATH.
+#ifndef VKRT_FAST_MATH
 // ---- ray generation: pathtrace.comp:97 / pathtrace.rgen:72 + pathtrace.glsl:348-376 -------------------
 __global__ void __launch_bounds__(256) raygenKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
                                                     const __grid_constant__ FrameParams fp)
@@ -95,6 +98,8 @@ __global__ void __launch_bounds__(256) raygenKernel(const __grid_constant__ Scen
   wf.absb[p]     = f4(0.f, 0.f, 0.f, 0.f);
   wf.queueCur[p] = p;
 }
+
+#endif  // !VKRT_FAST_MATH
 
 // ---- shading state from the hit: shade_state.glsl:63-145 -----------------------------------------------
 struct HitGeom
@@ -255,7 +260,7 @@ VKRT_D float spotAttenuation(float3 pointToLight, float3 spotDirection, float ou
 }
 
 // ---- env_sampling.glsl:38-135 -------------------------------------------------------------------------
-__device__ __noinline__ float3 environmentSample(const SceneView& sc, float3 xi, float3& toLight, float& pdf)
+static __device__ __noinline__ float3 environmentSample(const SceneView& sc, float3 xi, float3& toLight, float& pdf)
 {
   const uint32_t width = (uint32_t)sc.envW, height = (uint32_t)sc.envH;
   const uint32_t size  = width * height;
@@ -488,7 +493,7 @@ VKRT_D void bouncePhaseSample(const SceneView& sc, const FrameParams& fp, Bounce
   out.wantNext = (depth + 1 < maxDepth);
 }
 
-template <int PBR>
+template <int PBR, int FM>  // FM: distinct kernel symbols for the IEEE and the fast-math build of this file
 __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
                                                                             const __grid_constant__ FrameParams fp, TraceStats* stats)
 {
@@ -557,6 +562,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(cons
     atomicAdd(&stats->closestRays, (unsigned long long)count);
 }
 
+#ifndef VKRT_FAST_MATH
 // After the shadow pass of a bounce: next -> cur, reset cursors, count shadow rays.
 __global__ void swapQueuesKernel(Wavefront wf, TraceStats* stats)
 {
@@ -730,27 +736,36 @@ __global__ void __launch_bounds__(256) tonemapKernel(const float4* __restrict__ 
   }
 }
 
+#endif  // !VKRT_FAST_MATH
+
 // ---- launchers ---------------------------------------------------------------------------------------------
+#ifdef VKRT_FAST_MATH
+#define VKRT_SHADE_FM 1
+#define VKRT_LAUNCH_SHADE launchShadeFast
+#else
+#define VKRT_SHADE_FM 0
+#define VKRT_LAUNCH_SHADE launchShadePrecise
 void launchRaygen(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, int)
 {
   raygenKernel<<<(wf.numPaths + 255) / 256, 256, 0, s>>>(scene, wf, fp);
 }
+#endif
 template <int PBR>
 static void launchShadeT(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs)
 {
   static int perSM = 0;
   if(!perSM)
   {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shadeKernel<PBR>, kShadeBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shadeKernel<PBR, VKRT_SHADE_FM>, kShadeBlock, 0);
     if(perSM < 1) perSM = 1;
   }
   int grid = numSMs * perSM;
   int need = (int)((wf.numPaths + kShadeBlock - 1) / kShadeBlock);
   if(grid > need) grid = need;
   if(grid < 1) grid = 1;
-  shadeKernel<PBR><<<grid, kShadeBlock, 0, s>>>(scene, wf, fp, stats);
+  shadeKernel<PBR, VKRT_SHADE_FM><<<grid, kShadeBlock, 0, s>>>(scene, wf, fp, stats);
 }
-void launchShade(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs)
+void VKRT_LAUNCH_SHADE(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs)
 {
   // one kernel per BSDF model (RtxState.pbrMode, pathtrace.glsl:40-56): halves the code and register pressure
   if(fp.state.pbrMode == 0)
@@ -758,6 +773,7 @@ void launchShade(cudaStream_t s, const SceneView& scene, const Wavefront& wf, co
   else
     launchShadeT<1>(s, scene, wf, fp, stats, numSMs);
 }
+#ifndef VKRT_FAST_MATH
 void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats) { swapQueuesKernel<<<1, 1, 0, s>>>(wf, stats); }
 void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, int)
 {
@@ -775,5 +791,7 @@ void launchTonemap(cudaStream_t s, const float4* image, int w, int h, const Tone
 {
   tonemapKernel<<<(w * h + 255) / 256, 256, 0, s>>>(image, w, h, tm, mips, outF, out8);
 }
+
+#endif  // !VKRT_FAST_MATH
 
 }  // namespace vkrt

@@ -235,7 +235,7 @@ VKRT_D float nightBrightness(float3 sunDir)
 }
 
 // sun_and_sky.glsl:453-601
-__device__ __noinline__ float3 sunAndSky(const SunAndSky& ss, float3 inDirection)
+static __device__ __noinline__ float3 sunAndSky(const SunAndSky& ss, float3 inDirection)
 {
   float  factor = 1.0f, nightFactor = 1.0f;
   float3 rgbScale    = f3(ss.rgb_unit_conversion[0], ss.rgb_unit_conversion[1], ss.rgb_unit_conversion[2]);

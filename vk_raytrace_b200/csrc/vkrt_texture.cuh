@@ -36,7 +36,7 @@ VKRT_D float4 texel8(const TexDesc& t, int x, int y)
 }
 
 #ifdef VKRT_COMPACT_TEXTURE
-__device__ __noinline__ float4 sampleTexture(const TexDesc& t, float2 uv)
+static __device__ __noinline__ float4 sampleTexture(const TexDesc& t, float2 uv)
 #else
 VKRT_D float4 sampleTexture(const TexDesc& t, float2 uv)
 #endif
@@ -60,7 +60,7 @@ VKRT_D float4 sampleTexture(const TexDesc& t, float2 uv)
 }
 
 #ifdef VKRT_COMPACT_TEXTURE
-__device__ __noinline__ float3 sampleEnv(const SceneView& s, float2 uv)
+static __device__ __noinline__ float3 sampleEnv(const SceneView& s, float2 uv)
 #else
 VKRT_D float3 sampleEnv(const SceneView& s, float2 uv)
 #endif

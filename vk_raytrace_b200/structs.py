@@ -35,7 +35,7 @@ class SunAndSky(C.Structure):
 
 class RenderOpts(C.Structure):
     _fields_ = [("seed_mode", i32), ("frames_in_flight", i32), ("tile_size", i32), ("shard_rank", i32), ("shard_count", i32),
-                ("count_traversal", i32), ("sort_rays", i32), ("profile", i32), ("reserved", i32 * 8)]
+                ("count_traversal", i32), ("sort_rays", i32), ("profile", i32), ("precise_shading", i32), ("reserved", i32 * 7)]
 
 
 class Stats(C.Structure):
