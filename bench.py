@@ -137,7 +137,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sponza_1080p", choices=sorted(WORKLOADS))
     ap.add_argument("--pbr-mode", type=int, default=0)
-    ap.add_argument("--build-mode", type=int, default=1, help="0 LBVH, 1 LBVH + SAH leaf collapse (default), 2 host binned SAH")
+    ap.add_argument("--build-mode", type=int, default=-1,
+                    help="-1 auto (default): the best-tracing builder that is still quick at load time, as the reference asks its driver for "
+                         "(PREFER_FAST_TRACE, src/accelstruct.cpp:125): host binned SAH up to 2 M triangles, GPU LBVH + leaf collapse above; "
+                         "0 GPU LBVH, 1 GPU LBVH + SAH leaf collapse, 2 host binned SAH, 3 GPU PLOC + SAH leaf collapse")
     ap.add_argument("--frames-in-flight", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -180,6 +183,8 @@ def main():
     torch.cuda.set_device(device)
 
     scene = make_scene(cfg)
+    if args.build_mode < 0:
+        args.build_mode = 2 if scene.num_triangles() <= 2_000_000 else 1
     ctx = Context(device)
     upload_scene(ctx, scene, W, H, build_mode=args.build_mode)
     # the accumulation image lives in a torch tensor so that torch.distributed can reduce it over NVLink
@@ -338,6 +343,9 @@ def main():
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "scene": scene.name, "triangles": int(s.num_triangles), "bvh_nodes": int(s.num_bvh_nodes),
+                           "bvh_build": {"mode": {0: "lbvh", 1: "lbvh+leaf-collapse", 2: "host-sah", 3: "ploc+leaf-collapse"}[args.build_mode],
+                                         "ms": float(s.ms_build), "bvh_width": int(s.bvh_width), "max_depth": int(s.bvh_max_depth),
+                                         "what": "vkrt_scene_commit: instance flattening + BVH build, outside the timed region (SURVEY 8d)"},
                            "resolution": [W, H], "max_depth": cfg["depth"], "spp_per_step": 1, "pbr_mode": args.pbr_mode,
                            "sharding": f"{world} x interleaved 64x64 tiles" if use_dist else "none",
                            "l2": "per-step wavefront state (~170 B x %d paths) exceeds the 126 MB L2; the BVH/geometry is L2-resident by design" % (W * H),

@@ -43,6 +43,7 @@ typedef struct vkrt_ctx vkrt_ctx;
 #define VKRT_BUILD_LBVH 0       /* GPU Morton/Karras LBVH (default) */
 #define VKRT_BUILD_LBVH_COLLAPSED 1 /* LBVH + bottom-up SAH leaf collapse */
 #define VKRT_BUILD_SAH_HOST 2       /* GPU flatten + host binned-SAH BVH2 (slow build, fast trace) */
+#define VKRT_BUILD_PLOC 3           /* GPU: Morton sort + parallel locally-ordered clustering + SAH leaf collapse (SAH-like quality) */
 
 typedef struct vkrt_render_opts
 {

@@ -29,7 +29,8 @@ def both(vk, ob, gpu, scene, W, H, build_mode=0):
 
 
 # ---------------------------------------------------------------------------------------------- traversal
-@pytest.mark.parametrize("which,build_mode", [("cornell", 0), ("sponza", 0), ("sponza", 1), ("soup", 0), ("soup_mirrored_double", 1)])
+@pytest.mark.parametrize("which,build_mode", [("cornell", 0), ("sponza", 0), ("sponza", 1), ("soup", 0), ("soup_mirrored_double", 1),
+                                              ("cornell", 3), ("sponza", 3), ("soup", 3), ("soup_mirrored_double", 2)])
 def test_trace_rays_bit_exact(vk, ob, gpu, which, build_mode):
     from vk_raytrace_b200 import scenes
     sc = {"cornell": lambda: scenes.cornell_box(), "sponza": small_sponza, "soup": lambda: triangle_soup(500, 1),
@@ -261,7 +262,7 @@ def test_external_output_buffer_and_errors(vk, gpu):
         gpu.render(S.default_rtx_state(W, H, debugging_mode=12), 1)
 
 
-@pytest.mark.parametrize("build_mode", [0, 1])
+@pytest.mark.parametrize("build_mode", [0, 1, 3])
 def test_full_size_properties_sponza_1080p(vk, gpu, build_mode):
     """BASELINE.json configs[2] at full size (262k triangles, 1920x1080, depth 8): determinism, batching invariance,
     ray accounting, and agreement of sampled pixels with the oracle (the oracle only renders a band of rows)."""

@@ -65,6 +65,7 @@ struct vkrt_ctx
   GltfShadeMaterial*   dMat = nullptr;
   Light*               dLights = nullptr;
   TexDesc*             dTexDescs = nullptr;
+  AlphaMat*            dAlphaMats = nullptr;
   std::vector<uchar4*> dTexData;
   float4*              dEnv = nullptr;
   EnvAccel*            dEnvAccel = nullptr;
@@ -119,12 +120,12 @@ static int fail(vkrt_ctx* ctx, int code, const char* msg)
 static void freeScene(vkrt_ctx* c)
 {
   cudaFree(c->dVerts); cudaFree(c->dIdx); cudaFree(c->dGeo); cudaFree(c->dInst); cudaFree(c->dInstTriOffset);
-  cudaFree(c->dMat); cudaFree(c->dLights); cudaFree(c->dTexDescs);
+  cudaFree(c->dMat); cudaFree(c->dLights); cudaFree(c->dTexDescs); cudaFree(c->dAlphaMats);
   for(auto p : c->dTexData) cudaFree(p);
   c->dTexData.clear();
   cudaFree(c->bvh.nodes); cudaFree(c->bvh.qnodes); cudaFree(c->bvh.cnodes); cudaFree(c->bvh.wnodes); cudaFree(c->bvh.triInfo); cudaFree(c->bvh.triShade);
   c->dVerts = nullptr; c->dIdx = nullptr; c->dGeo = nullptr; c->dInst = nullptr; c->dInstTriOffset = nullptr;
-  c->dMat = nullptr; c->dLights = nullptr; c->dTexDescs = nullptr;
+  c->dMat = nullptr; c->dLights = nullptr; c->dTexDescs = nullptr; c->dAlphaMats = nullptr;
   c->bvh = BvhResult{};
   c->committed = false;
 }
@@ -342,6 +343,8 @@ int vkrt_scene_add_texture(vkrt_ctx* ctx, const uint8_t* rgba8, uint32_t width, 
 
 int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
 {
+  if(ctx && (build_mode < VKRT_BUILD_LBVH || build_mode > VKRT_BUILD_PLOC))
+    return fail(ctx, VKRT_ERR_INVALID, "scene_commit: unknown build mode");
   if(!ctx) return VKRT_ERR_INVALID;
   cudaSetDevice(ctx->device);
   if(ctx->materials.empty())
@@ -458,10 +461,29 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
   CTX_CHECK(cudaMalloc(&ctx->dTexDescs, sizeof(TexDesc) * std::max<size_t>(descs.size(), 1)));
   if(!descs.empty())
     CTX_CHECK(cudaMemcpyAsync(ctx->dTexDescs, descs.data(), sizeof(TexDesc) * descs.size(), cudaMemcpyHostToDevice, ctx->stream));
+  // alpha records for the any-hit test (HitTest, shaders/traceray_rq.glsl:32-102): everything it reads from the material
+  std::vector<AlphaMat> alphaMats(ctx->materials.size());
+  for(size_t i = 0; i < ctx->materials.size(); i++)
+  {
+    const GltfShadeMaterial& m = ctx->materials[i];
+    AlphaMat&                a = alphaMats[i];
+    std::memset(&a, 0, sizeof(a));
+    a.alphaFactor = m.pbrBaseColorFactor[3];
+    a.alphaCutoff = m.alphaCutoff;
+    a.alphaMode   = m.alphaMode;
+    a.hasTexture  = (m.pbrBaseColorTexture > -1 && (size_t)m.pbrBaseColorTexture < descs.size()) ? 1 : 0;
+    std::memcpy(a.uvRows, m.uvTransform, sizeof(a.uvRows));
+    if(a.hasTexture)
+      a.texture = descs[m.pbrBaseColorTexture];
+  }
+  CTX_CHECK(cudaMalloc(&ctx->dAlphaMats, sizeof(AlphaMat) * std::max<size_t>(alphaMats.size(), 1)));
+  if(!alphaMats.empty())
+    CTX_CHECK(cudaMemcpyAsync(ctx->dAlphaMats, alphaMats.data(), sizeof(AlphaMat) * alphaMats.size(), cudaMemcpyHostToDevice, ctx->stream));
 
   // acceleration structure
   std::string berr;
   uint64_t    launches = 0;
+  cudaEventRecord(e0, ctx->stream);  // ms_build: the acceleration structure only (flatten, sort, hierarchy, refit, emit, node formats)
   if(!buildBvh(ctx->stream, ctx->dInst, ctx->dInstTriOffset, (uint32_t)inst.size(), ctx->dGeo, (uint32_t)totalTris, build_mode, ctx->bvh, berr, &launches))
   {
     ctx->err = "scene_commit: BVH build failed: " + berr;
@@ -487,6 +509,8 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
     CTX_CHECK(cudaMemcpy(ctx->bvh.tris, sorted.data(), sorted.size() * sizeof(float), cudaMemcpyHostToDevice));
     ctx->bvh.maxDepth = depth;
   }
+  if(ctx->bvh.maxDepth > 120)
+    return fail(ctx, VKRT_ERR_INVALID, "scene_commit: the BVH is deeper than the traversal stack (128 entries)");
   if(!quantizeBvh(ctx->stream, ctx->bvh, berr, &launches))
   {
     ctx->err = "scene_commit: BVH node quantisation failed: " + berr;
@@ -507,9 +531,10 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
   ctx->stats.ms_build       = ms;
   ctx->stats.num_triangles  = (uint32_t)totalTris;
   ctx->stats.num_bvh_nodes  = ctx->bvh.numNodes;
-  ctx->stats.node_bytes     = (uint32_t)traceNodeBytes();
-  ctx->stats.bvh_width      = (uint32_t)traceBvhWidth();
-  if(traceBvhWidth() == 4)
+  const int width           = traceBvhWidth((uint32_t)totalTris);
+  ctx->stats.node_bytes     = (uint32_t)traceNodeBytes(width);
+  ctx->stats.bvh_width      = (uint32_t)width;
+  if(width == 4)
     ctx->stats.num_bvh_nodes = ctx->bvh.numWideNodes;
   ctx->stats.num_instances  = (uint32_t)inst.size();
   ctx->stats.has_non_opaque = nonOpaque ? 1u : 0u;
@@ -548,9 +573,11 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
   v.instances    = ctx->dInst;
   v.geoInfo      = ctx->dGeo;
   v.materials    = ctx->dMat;
+  v.alphaMats    = ctx->dAlphaMats;
   v.lights       = ctx->dLights;
   v.textures     = ctx->dTexDescs;
   v.numTris      = (uint32_t)totalTris;
+  v.bvhWidth     = (uint32_t)width;
   v.hasNonOpaque = nonOpaque ? 1u : 0u;
   ctx->committed = true;
   return VKRT_OK;

@@ -74,7 +74,7 @@ __global__ void flattenKernel(const InstanceXform* __restrict__ inst, const uint
     float3 v2 = xformPoint(I.o2w, f3(pc[0], pc[1], pc[2]));
     wtri[3ull * gid + 0] = f4(v0, __uint_as_float(I.flags));
     wtri[3ull * gid + 1] = f4(v1, __uint_as_float(gid));
-    wtri[3ull * gid + 2] = f4(v2, 0.f);
+    wtri[3ull * gid + 2] = f4(v2, __uint_as_float((uint32_t)max(0, g.materialIndex)));  // for the any-hit alpha test
     triInfo[gid]         = make_uint2(lo, prim);
     // per-triangle shading record: the three 32-byte vertices + {instance, material}; one dependent load from the hit
     // instead of triInfo -> instance -> geometry -> indices -> vertices
@@ -268,6 +268,180 @@ __global__ void refitKernel(const float4* __restrict__ wtri, const uint32_t* __r
       *maxDepthOut = depth;
     __threadfence();
     node = parentInner[node];
+  }
+}
+
+// ---- 4b. PLOC topology (Meister & Bittner 2017): parallel locally-ordered clustering ----------------------
+// An alternative to the Karras hierarchy with SAH-like quality.  The Morton-sorted leaves are the initial clusters; every
+// round each cluster looks R places left and right for the neighbour whose union box has the smallest area, mutual nearest
+// neighbours merge, and the survivors are compacted in place (order is kept, so Morton locality survives).  ~40 % of the
+// clusters disappear per round.  The result is written in the conventions of hierarchyKernel (root = node 0, child codes,
+// parent arrays, [first,last] leaf ranges) after the leaves have been renumbered in depth-first order, so that refitKernel /
+// emitKernel and the multi-triangle leaf collapse run unchanged.
+// search radius: 16 while there are many clusters; wider near the top of the tree, where every ray passes and the Morton
+// order says little about which big clusters belong together
+static int plocRadius(int c) { (void)c; return 16; }  // wider windows near the top were measured and traced worse (profiles/README.md)
+
+__global__ void plocInitKernel(const float4* __restrict__ wtri, const uint32_t* __restrict__ sortedVals, int n, int* __restrict__ cid,
+                               Box* __restrict__ cbox, int* __restrict__ csize)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if(j >= n)
+    return;
+  const uint32_t gid = sortedVals[j];
+  const float4   a = wtri[3ull * gid], b = wtri[3ull * gid + 1], c = wtri[3ull * gid + 2];
+  Box bx;
+  bx.lo[0] = fminf(a.x, fminf(b.x, c.x)); bx.lo[1] = fminf(a.y, fminf(b.y, c.y)); bx.lo[2] = fminf(a.z, fminf(b.z, c.z));
+  bx.hi[0] = fmaxf(a.x, fmaxf(b.x, c.x)); bx.hi[1] = fmaxf(a.y, fmaxf(b.y, c.y)); bx.hi[2] = fmaxf(a.z, fmaxf(b.z, c.z));
+  cid[j]   = ~j;
+  cbox[j]  = bx;
+  csize[j] = 1;
+}
+
+__device__ __forceinline__ float unionArea(const Box& a, const Box& b)
+{
+  const float ex = fmaxf(a.hi[0], b.hi[0]) - fminf(a.lo[0], b.lo[0]);
+  const float ey = fmaxf(a.hi[1], b.hi[1]) - fminf(a.lo[1], b.lo[1]);
+  const float ez = fmaxf(a.hi[2], b.hi[2]) - fminf(a.lo[2], b.lo[2]);
+  return ex * ey + ey * ez + ez * ex;
+}
+
+// nn[i] = argmin over the window of (union area, j): ascending scan + strict '<' makes the globally best pair mutual, so
+// every round merges at least one pair.  forcePair (slow progress, e.g. thousands of identical boxes): neighbours 2k, 2k+1.
+__global__ void plocNearestKernel(const Box* __restrict__ cbox, int c, int* __restrict__ nn, int forcePair, int radius)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= c)
+    return;
+  if(forcePair)
+  {
+    const int j = i ^ 1;
+    nn[i]       = j < c ? j : -1;
+    return;
+  }
+  const Box me   = cbox[i];
+  int       best = -1;
+  float     bd   = FLT_MAX;
+  const int j0 = max(0, i - radius), j1 = min(c - 1, i + radius);
+  for(int j = j0; j <= j1; j++)
+  {
+    if(j == i)
+      continue;
+    const float d = unionArea(me, cbox[j]);
+    if(d < bd || best < 0)
+    {
+      bd   = d;
+      best = j;
+    }
+  }
+  nn[i] = best;
+}
+
+__global__ void plocMergeKernel(const int* __restrict__ cid, const Box* __restrict__ cbox, const int* __restrict__ csize,
+                                const int* __restrict__ nn, int c, int n, int* __restrict__ nodeCounter, int2* __restrict__ children,
+                                int* __restrict__ parentInner, int* __restrict__ parentLeaf, int* __restrict__ nodeSize,
+                                int* __restrict__ cidOut, Box* __restrict__ boxOut, int* __restrict__ sizeOut, uint32_t* __restrict__ valid)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= c)
+    return;
+  const int  j      = nn[i];
+  const bool mutual = j >= 0 && nn[j] == i;
+  if(!mutual)
+  {
+    valid[i]   = 1u;
+    cidOut[i]  = cid[i];
+    boxOut[i]  = cbox[i];
+    sizeOut[i] = csize[i];
+    return;
+  }
+  if(i > j)
+  {
+    valid[i] = 0u;
+    return;
+  }
+  const int idx = (n - 2) - atomicAdd(nodeCounter, 1);  // the last merge becomes node 0, the root
+  const int a = cid[i], b = cid[j];
+  children[idx] = make_int2(a, b);
+  if(a >= 0) parentInner[a] = idx; else parentLeaf[~a] = idx;
+  if(b >= 0) parentInner[b] = idx; else parentLeaf[~b] = idx;
+  const Box x = cbox[i], y = cbox[j];
+  Box       u;
+#pragma unroll
+  for(int k = 0; k < 3; k++)
+  {
+    u.lo[k] = fminf(x.lo[k], y.lo[k]);
+    u.hi[k] = fmaxf(x.hi[k], y.hi[k]);
+  }
+  const int sz  = csize[i] + csize[j];
+  nodeSize[idx] = sz;
+  valid[i]      = 1u;
+  cidOut[i]     = idx;
+  boxOut[i]     = u;
+  sizeOut[i]    = sz;
+}
+
+__global__ void plocCompactKernel(const uint32_t* __restrict__ valid, const uint32_t* __restrict__ pos, int c, const int* __restrict__ cidIn,
+                                  const Box* __restrict__ boxIn, const int* __restrict__ sizeIn, int* __restrict__ cid, Box* __restrict__ cbox,
+                                  int* __restrict__ csize, int* __restrict__ newCount)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= c)
+    return;
+  if(valid[i])
+  {
+    const uint32_t p = pos[i];
+    cid[p]   = cidIn[i];
+    cbox[p]  = boxIn[i];
+    csize[p] = sizeIn[i];
+  }
+  if(i == c - 1)
+    *newCount = (int)(pos[i] + valid[i]);
+}
+
+// depth-first position of a leaf / first leaf of an inner node: the sizes of the left siblings on the way up
+__device__ __forceinline__ int plocOffset(int code, int parent, const int2* __restrict__ children, const int* __restrict__ parentInner,
+                                          const int* __restrict__ nodeSize)
+{
+  int off = 0, cur = code, p = parent;
+  while(p >= 0)
+  {
+    const int2 ch = children[p];
+    if(ch.y == cur)
+      off += ch.x >= 0 ? nodeSize[ch.x] : 1;
+    cur = p;
+    p   = parentInner[p];
+  }
+  return off;
+}
+__global__ void plocOrderKernel(int n, const int2* __restrict__ children, const int* __restrict__ parentInner, const int* __restrict__ parentLeaf,
+                                const int* __restrict__ nodeSize, int* __restrict__ leafPos, int2* __restrict__ ranges)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n)
+    leafPos[i] = plocOffset(~i, parentLeaf[i], children, parentInner, nodeSize);
+  if(i < n - 1)
+  {
+    const int off = plocOffset(i, parentInner[i], children, parentInner, nodeSize);
+    ranges[i]     = make_int2(off, off + nodeSize[i] - 1);
+  }
+}
+__global__ void plocRemapKernel(int n, int2* __restrict__ children, const int* __restrict__ leafPos, const uint32_t* __restrict__ sortedVals,
+                                uint32_t* __restrict__ sortedOut, const int* __restrict__ parentLeafOld, int* __restrict__ parentLeafNew)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < n)
+  {
+    const int p      = leafPos[i];
+    sortedOut[p]     = sortedVals[i];
+    parentLeafNew[p] = parentLeafOld[i];
+  }
+  if(i < n - 1)
+  {
+    int2 ch = children[i];
+    if(ch.x < 0) ch.x = ~leafPos[~ch.x];
+    if(ch.y < 0) ch.y = ~leafPos[~ch.y];
+    children[i] = ch;
   }
 }
 
@@ -565,6 +739,70 @@ fail:
   return false;
 }
 
+// PLOC driver: fills children / ranges / parentInner / parentLeaf (hierarchyKernel conventions) and sortedOut (leaf order).
+static bool plocTopology(cudaStream_t stream, const float4* wtri, const uint32_t* sortedVals, int n, int2* children, int2* ranges,
+                         int* parentInner, int* parentLeaf, uint32_t* sortedOut, std::string& err, uint64_t* launches, int* roundsOut)
+{
+  int *cid = nullptr, *cidT = nullptr, *csize = nullptr, *csizeT = nullptr, *nn = nullptr, *nodeSize = nullptr, *counters = nullptr;
+  int *leafPos = nullptr, *parentLeafOld = nullptr;
+  Box *cbox = nullptr, *cboxT = nullptr;
+  uint32_t *valid = nullptr, *pos = nullptr;
+  void*     scanTemp = nullptr;
+  size_t    scanBytes = 0;
+  const int B = 256;
+  int       c = n, rounds = 0, forcePair = 0;
+  CK(cudaMalloc(&cid, 4ull * n)); CK(cudaMalloc(&cidT, 4ull * n)); CK(cudaMalloc(&csize, 4ull * n)); CK(cudaMalloc(&csizeT, 4ull * n));
+  CK(cudaMalloc(&nn, 4ull * n)); CK(cudaMalloc(&nodeSize, 4ull * n)); CK(cudaMalloc(&counters, 8));
+  CK(cudaMalloc(&leafPos, 4ull * n)); CK(cudaMalloc(&parentLeafOld, 4ull * n));
+  CK(cudaMalloc(&cbox, sizeof(Box) * (size_t)n)); CK(cudaMalloc(&cboxT, sizeof(Box) * (size_t)n));
+  CK(cudaMalloc(&valid, 4ull * n)); CK(cudaMalloc(&pos, 4ull * n));
+  CK(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, valid, pos, n, stream));
+  CK(cudaMalloc(&scanTemp, scanBytes ? scanBytes : 16));
+  CK(cudaMemsetAsync(counters, 0, 8, stream));
+  plocInitKernel<<<(n + B - 1) / B, B, 0, stream>>>(wtri, sortedVals, n, cid, cbox, csize);
+  if(launches) (*launches)++;
+  while(c > 1)
+  {
+    const int grid = (c + B - 1) / B;
+    plocNearestKernel<<<grid, B, 0, stream>>>(cbox, c, nn, forcePair, plocRadius(c));
+    plocMergeKernel<<<grid, B, 0, stream>>>(cid, cbox, csize, nn, c, n, counters, children, parentInner, parentLeafOld, nodeSize, cidT, cboxT,
+                                             csizeT, valid);
+    CK(cub::DeviceScan::ExclusiveSum(scanTemp, scanBytes, valid, pos, c, stream));
+    plocCompactKernel<<<grid, B, 0, stream>>>(valid, pos, c, cidT, cboxT, csizeT, cid, cbox, csize, counters + 1);
+    if(launches) (*launches) += 4;
+    int next = 0;
+    CK(cudaMemcpyAsync(&next, counters + 1, 4, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    if(next < 1 || next >= c || ++rounds > 100000)
+    {
+      err = "plocTopology: no progress";
+      goto fail;
+    }
+    // a round normally removes 30-40 % of the clusters.  Only a degenerate input (thousands of identical boxes) merges one pair
+    // per round; with many clusters left that would take forever, so neighbours are paired up for one round instead
+    forcePair = (c > 1024 && (long long)(c - next) * 256 < c) ? 1 : 0;
+    c         = next;
+  }
+  {
+    const int root = -1;
+    CK(cudaMemcpyAsync(parentInner, &root, 4, cudaMemcpyHostToDevice, stream));  // node 0 is the root
+    const int grid = (n + B - 1) / B;
+    plocOrderKernel<<<grid, B, 0, stream>>>(n, children, parentInner, parentLeafOld, nodeSize, leafPos, ranges);
+    plocRemapKernel<<<grid, B, 0, stream>>>(n, children, leafPos, sortedVals, sortedOut, parentLeafOld, parentLeaf);
+    if(launches) (*launches) += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(stream));
+  }
+  if(roundsOut) *roundsOut = rounds;
+  cudaFree(cid); cudaFree(cidT); cudaFree(csize); cudaFree(csizeT); cudaFree(nn); cudaFree(nodeSize); cudaFree(counters);
+  cudaFree(leafPos); cudaFree(parentLeafOld); cudaFree(cbox); cudaFree(cboxT); cudaFree(valid); cudaFree(pos); cudaFree(scanTemp);
+  return true;
+fail:
+  cudaFree(cid); cudaFree(cidT); cudaFree(csize); cudaFree(csizeT); cudaFree(nn); cudaFree(nodeSize); cudaFree(counters);
+  cudaFree(leafPos); cudaFree(parentLeafOld); cudaFree(cbox); cudaFree(cboxT); cudaFree(valid); cudaFree(pos); cudaFree(scanTemp);
+  return false;
+}
+
 // Host driver.  All temporaries are freed before returning; nodes/tris/triInfo are owned by the caller.
 bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* dInstTriOffset, uint32_t numInst, const InstanceData* dGeo,
               uint32_t numTris, int buildMode, BvhResult& out, std::string& err, uint64_t* launches)
@@ -626,9 +864,17 @@ bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* d
     CK(cub::DeviceRadixSort::SortPairs(cubTemp, tempBytes, dk, dv, (int)n, 0, 63, stream));
     const uint64_t* sk = dk.Current();
     const uint32_t* sv = dv.Current();
-    if(n > 1)
+    if(n > 1 && buildMode == VKRT_BUILD_PLOC)
+    {
+      // the other key buffer is free after the sort: it receives the depth-first leaf order
+      uint32_t* svOut = (dv.Current() == valsA) ? valsB : valsA;
+      if(!plocTopology(stream, wtri, sv, (int)n, children, ranges, parentInner, parentLeaf, svOut, err, launches, nullptr))
+        goto fail;
+      sv = svOut;
+    }
+    else if(n > 1)
       hierarchyKernel<<<grid, B, 0, stream>>>(sk, (int)n, children, ranges, parentInner, parentLeaf);
-    int collapseMax = buildMode == VKRT_BUILD_LBVH_COLLAPSED ? 8 : 1;
+    int collapseMax = (buildMode == VKRT_BUILD_LBVH_COLLAPSED || buildMode == VKRT_BUILD_PLOC) ? 8 : 1;
     refitKernel<<<grid, B, 0, stream>>>(wtri, sv, (int)n, out.tris, children, parentInner, parentLeaf, leafBox, nodeBox, nodeCost,
                                        nodeDepth, collapsed, ranges, flags, collapseMax, maxDepthDev);
     emitKernel<<<grid, B, 0, stream>>>((int)n, children, ranges, leafBox, nodeBox, collapsed, out.nodes);

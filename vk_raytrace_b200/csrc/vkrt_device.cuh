@@ -39,6 +39,19 @@ struct TexDesc
   int32_t       _pad;
 };
 
+// What the any-hit alpha test needs from a material, in one place (80 bytes, by material index): the traversal kernels
+// reach it from the triangle record alone, in parallel with the triangle's texture coordinates, instead of walking
+// triangle -> instance -> geometry -> material -> texture table.
+struct AlphaMat
+{
+  float   alphaFactor;  // pbrBaseColorFactor.a
+  float   alphaCutoff;
+  int32_t alphaMode;
+  int32_t hasTexture;   // pbrBaseColorTexture > -1
+  float   uvRows[8];    // the two rows of uvTransform that applyUvTransform reads
+  TexDesc texture;
+};
+
 struct SceneView
 {
   // traversal
@@ -54,12 +67,14 @@ struct SceneView
   const InstanceXform*     instances;
   const InstanceData*      geoInfo;    // per primMesh: reference layout, CUDA pointers
   const GltfShadeMaterial* materials;
+  const AlphaMat*          alphaMats;  // by material index
   const Light*             lights;
   const TexDesc*           textures;
   const float4*            envPixels;
   const EnvAccel*          envAccel;
   int32_t                  envW, envH;
   uint32_t                 numTris;
+  uint32_t                 bvhWidth;   // 2 or 4: which tree the trace kernels walk for this scene
   uint32_t                 hasNonOpaque;
   SceneCamera              camera;
   SunAndSky                sunsky;

@@ -55,8 +55,8 @@ struct TraceLaunch
   float4*         rad;
   TraceStats*     stats;      // nullptr unless counting
 };
-int  traceBvhWidth();   // 2 or 4: tree width of the active traversal kernel
-int  traceNodeBytes();  // 32 or 64: node format of the active traversal kernel
+int  traceBvhWidth(uint32_t numTris);  // 2 or 4: tree the trace kernels walk for a scene of this size (VKRT_BVH_WIDTH)
+int  traceNodeBytes(int bvhWidth);     // bytes per node the trace kernels fetch: 64, or 32 with VKRT_NODE_FORMAT=q32
 void launchTraceClosest(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, bool count, int numSMs);
 void launchTraceShadow(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, bool count, int numSMs);
 void launchTraceAnyProbe(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, int numSMs);

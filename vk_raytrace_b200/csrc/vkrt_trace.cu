@@ -54,27 +54,23 @@ constexpr unsigned kFull             = 0xffffffffu;
 enum TraceMode { MODE_CLOSEST = 0, MODE_SHADOW_RESOLVE = 1, MODE_ANY_PROBE = 2 };
 
 // ---- alpha test for non-FORCE_OPAQUE instances (cold path) --------------------------------
-__device__ __noinline__ bool alphaTestPasses(const SceneView& sc, uint32_t triId, float bu, float bv, uint32_t raySeed)
+__device__ __noinline__ bool alphaTestPasses(const SceneView& sc, uint32_t triId, uint32_t matId, float bu, float bv, uint32_t raySeed)
 {
-  const uint2              info = __ldg(&sc.triInfo[triId]);
-  const InstanceXform&     I    = sc.instances[info.x];
-  const InstanceData       geo  = sc.geoInfo[I.primMesh];
-  const GltfShadeMaterial& mat  = sc.materials[max(0, geo.materialIndex)];
-  float                    baseColorAlpha = mat.pbrBaseColorFactor[3];
-  const int                texId = mat.pbrBaseColorTexture;
-  if(texId > -1)
+  // two independent gathers (the material's alpha record, the triangle's texture coordinates), then the texels
+  const AlphaMat& am = sc.alphaMats[matId];
+  const uint4*    ts = sc.triShade + 7ull * triId;  // {pos, n | uv, tangent, colour} x 3, see flattenKernel
+  const uint4     a1 = __ldg(ts + 1), b1 = __ldg(ts + 3), c1 = __ldg(ts + 5);
+  float           baseColorAlpha = am.alphaFactor;
+  if(am.hasTexture)
   {
-    const uint32_t*         idx = reinterpret_cast<const uint32_t*>(geo.indexAddress) + 3ull * info.y;
-    const VertexAttributes* vtx = reinterpret_cast<const VertexAttributes*>(geo.vertexAddress);
-    const float*            t0  = vtx[idx[0]].texcoord;
-    const float*            t1  = vtx[idx[1]].texcoord;
-    const float*            t2  = vtx[idx[2]].texcoord;
-    const float             b0  = 1.0f - bu - bv;
-    float2 tc = f2(t0[0], t0[1]) * b0 + f2(t1[0], t1[1]) * bu + f2(t2[0], t2[1]) * bv;
-    tc        = applyUvTransform(mat.uvTransform, tc);
-    baseColorAlpha *= sampleTexture(sc.textures[texId], tc).w;
+    // texcoord as stored (the tangent handedness bit in v's LSB included, as traceray_rq.glsl:72-83 reads it)
+    const float b0 = 1.0f - bu - bv;
+    float2      tc = f2(__uint_as_float(a1.x), __uint_as_float(a1.y)) * b0 + f2(__uint_as_float(b1.x), __uint_as_float(b1.y)) * bu
+                + f2(__uint_as_float(c1.x), __uint_as_float(c1.y)) * bv;
+    tc             = applyUvTransform(am.uvRows, tc);
+    baseColorAlpha *= sampleTexture(am.texture, tc).w;
   }
-  float opacity = (mat.alphaMode == VKRT_ALPHA_MASK) ? (baseColorAlpha > mat.alphaCutoff ? 1.0f : 0.0f) : baseColorAlpha;
+  float opacity = (am.alphaMode == VKRT_ALPHA_MASK) ? (baseColorAlpha > am.alphaCutoff ? 1.0f : 0.0f) : baseColorAlpha;
   return !(alphaDraw(raySeed, triId) > opacity);
 }
 
@@ -381,7 +377,7 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
             // t in (0, tmax): bestT starts at tmax, so only the tie branch has to exclude "no hit yet"
             if(!(t > 0.0f && (t < bestT || (t == bestT && bestTri != ~0u && triId < bestTri))))
               continue;
-            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, u, v, __float_as_uint(L.rayD[slot].w)))
+            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, __float_as_uint(q2.w), u, v, __float_as_uint(L.rayD[slot].w)))
               continue;
             bestT = t; bestU = u; bestV = v; bestTri = triId;
             if(MODE != MODE_CLOSEST)
@@ -647,7 +643,7 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_WIDE_MINBLOCKS) traceKernelW
             const float t = dot(e2, q) * inv;
             if(!(t > 0.0f && (t < bestT || (t == bestT && bestTri != ~0u && triId < bestTri))))
               continue;
-            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, u, v, __float_as_uint(L.rayD[slot].w)))
+            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, __float_as_uint(q2.w), u, v, __float_as_uint(L.rayD[slot].w)))
               continue;
             bestT = t; bestU = u; bestV = v; bestTri = triId;
             if(MODE != MODE_CLOSEST)
@@ -874,7 +870,7 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernelIfIf(const __grid_c
               continue;
             if(!(t < bestT || (t == bestT && triId < bestTri)))
               continue;
-            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, u, v, seed))
+            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, __float_as_uint(q2.w), u, v, seed))
               continue;
             bestT = t; bestU = u; bestV = v; bestTri = triId;
             if(MODE != MODE_CLOSEST)
@@ -1170,7 +1166,7 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernelCoop(const __grid_c
             const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | triId;
             if(!(key < cur && key < cand))
               continue;
-            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, u, v, rseed))
+            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, __float_as_uint(q2.w), u, v, rseed))
               continue;
             cand = key; cu = u; cv = v;
           }
@@ -1286,7 +1282,7 @@ int traceNodeFormat()
   }
   return fmt;
 }
-int traceNodeBytes() { return (traceBvhWidth() == 4) ? 64 : (traceNodeFormat() == FMT_Q32 ? 32 : 64); }
+int traceNodeBytes(int bvhWidth) { return (bvhWidth == 4) ? 64 : (traceNodeFormat() == FMT_Q32 ? 32 : 64); }
 template <int MODE, bool COUNT>
 static void launchTraceWide(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, int numSMs)
 {
@@ -1299,22 +1295,27 @@ static void launchTraceWide(cudaStream_t s, const SceneView& scene, const TraceL
   }
   traceKernelWide<MODE, COUNT><<<grid, kTraceBlock, 0, s>>>(scene, L);
 }
-// Tree width of the active traversal kernel: 2 (binary, default) or 4 via VKRT_BVH_WIDTH.
-int traceBvhWidth()
+// Tree width for a scene (VKRT_BVH_WIDTH = 2 | 4 | auto, default auto): the binary tree while the BVH fits the L2, the 4-wide
+// tree (half as many dependent fetches per ray) once it is HBM resident -- measured: equal on the 263 k-triangle scene,
+// +9 % on the 10 M-triangle one.  The experimental loop variants only exist for the binary tree.
+int traceBvhWidth(uint32_t numTris)
 {
-  static int width = 0;
-  if(!width)
+  static int mode = -1;  // 0 auto, 2, 4
+  if(mode < 0)
   {
     const char* e = getenv("VKRT_BVH_WIDTH");
     const char* v = getenv("VKRT_TRACE_VARIANT");
-    width         = (e && atoi(e) == 4 && !(v && atoi(v) != 8)) ? 4 : 2;
+    mode          = (e && atoi(e) == 4) ? 4 : ((e && atoi(e) == 2) ? 2 : 0);
+    if(v && atoi(v) != 8) mode = 2;
   }
-  return width;
+  if(mode == 0)
+    return numTris > 1500000u ? 4 : 2;
+  return mode;
 }
 template <int MODE, bool COUNT>
 static void launchTrace(cudaStream_t s, const SceneView& scene, const TraceLaunch& L, int numSMs)
 {
-  if(traceBvhWidth() == 4)
+  if(scene.bvhWidth == 4)
   {
     launchTraceWide<MODE, COUNT>(s, scene, L, numSMs);
     return;
