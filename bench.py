@@ -56,7 +56,31 @@ class ClockSampler(threading.Thread):
         self.stop_flag = threading.Event()
         self.max_mhz = None
 
+    def _run_nvml(self):
+        """NVML polling every 10 ms (the timed region of the default run is ~0.1 s; nvidia-smi takes that long per call)."""
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        try:
+            reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons
+        except AttributeError:
+            reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag.is_set():
+            self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            mask = int(reasons(h))
+            for n, b in bits.items():
+                if mask & b:
+                    self.reasons.add(n)
+            self.stop_flag.wait(0.01)
+
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -277,11 +301,6 @@ def main():
             traffic = json.load(open(prof)).get("traceClosestKernel_dram_bytes_per_launch")
         except Exception:
             traffic = None
-    # the resource that actually binds the traversal: the L1 data pipe serves one cache-line wavefront per clock per SM and a
-    # node step of a lane costs node_bytes / 32 of them (32-B quantised node: one; fp32 node: two), see profiles/README.md
-    sm_clk = (sampler.summary()["sm_mhz"] or 1965.0) * 1e6
-    steps_per_s = c_nodes / max(kernel_ms["trace_closest"], 1e-9) * 1e3
-    l1_peak = 148 * sm_clk * (32.0 / node_bytes)
     roofline = {"kernel": "traceKernel<CLOSEST>", "bound": "hbm", "achieved": ach_closest, "peak": peak, "unit": "GB/s", "frac": ach_closest / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "per_ray": {"node_bytes": node_bytes, "nodes": c_nodes / max(1, sc.closest_rays), "tris": c_tris / max(1, sc.closest_rays),
@@ -289,12 +308,10 @@ def main():
                 "shadow_kernel": {"achieved": ach_shadow, "frac": ach_shadow / peak,
                                   "nodes_per_ray": sc.shadow_nodes_visited / max(1, sc.shadow_rays),
                                   "tris_per_ray": sc.shadow_tris_tested / max(1, sc.shadow_rays)},
-                "l1_gather": {"achieved_gsteps_per_s": steps_per_s / 1e9, "peak_gsteps_per_s": l1_peak / 1e9, "frac": steps_per_s / l1_peak,
-                              "what": "BVH node steps/s vs 148 SMs x SM clock x (32 B / node bytes): the L1 serves one 32-byte-per-lane wavefront per clock per SM"},
-                "note": "algorithmic bytes (SURVEY 8d) / summed CUDA-event kernel time.  For L2-resident scenes (this one: 30 MB BVH) the "
-                        "algorithmic rate exceeds the HBM peak because node traffic is served by L1/L2; DRAM traffic (`traffic`, ncu) is only "
-                        "the ray/hit streams.  The kernel is bound by L1 gather wavefronts (l1_gather), not by HBM; the HBM-resident case is "
-                        "the instanced_10m workload."}
+                "note": "algorithmic bytes (SURVEY 8d) / summed CUDA-event kernel time of the serialised pass.  For L2-resident scenes "
+                        "(this one: 30 MB BVH) the algorithmic rate exceeds the HBM peak because node traffic is served by L1/L2; DRAM "
+                        "traffic (`traffic`, ncu, bounce-0 launch) is the ray / hit streams only.  What bounds the kernel is the latency of "
+                        "the dependent node fetches at 32 warps per SM (profiles/README.md); the HBM-resident case is instanced_10m."}
 
     # ---- e2e: host buffers in, host image out, every step through the C ABI (rank-local; N=1 only)
     e2e = None

@@ -330,6 +330,19 @@ def test_fast_shading_against_precise_and_oracle(vk, ob, gpu, pbr):
             assert bad.mean() <= 0.002, (dbg, bad.mean())
 
 
+@pytest.mark.parametrize("env", [{"VKRT_BVH_WIDTH": "4"}, {"VKRT_NODE_FORMAT": "q32"}, {"VKRT_NODE_FORMAT": "lohi"}, {"VKRT_TRACE_VARIANT": "200"},
+                                 {"VKRT_OVERLAP": "0"}])
+def test_non_default_traversal_kernels_in_subprocess(env):
+    """The traversal kernel is chosen once per process (environment): the 4-wide tree, the 16-bit grid nodes, the min/max fp32
+    nodes, the if-if loop and the single-stream schedule must give the same bit-exact hits and the same images as the default."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-m", "gpu", "-x", "-q",
+                          "-k", "trace_rays_bit_exact or degenerate or cornell_matches or sponza_with_alpha"],
+                         capture_output=True, text=True, cwd=root, timeout=600, env=dict(os.environ, **env))
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_cpp_renderer_adaptor_headless(vk):
     """`CudaRenderer : Renderer` (vk_raytrace_b200/host/) driven like src/main.cpp drives a back-end."""
     import subprocess

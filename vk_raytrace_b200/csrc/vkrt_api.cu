@@ -828,7 +828,7 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
     return VKRT_OK;
   int fif = o.frames_in_flight;
   if(fif <= 0)
-    fif = (int)std::max<size_t>(1, std::min<size_t>(64, (size_t)(32u << 20) / nLocal));  // ~32 M paths (5.4 GB of wavefront state): amortises the latency floor of thin late bounces
+    fif = (int)std::max<size_t>(1, std::min<size_t>(64, (size_t)(64u << 20) / nLocal));  // ~64 M paths (11 GB of wavefront state): amortises the latency floor of thin late bounces
   // the wavefront is sized for the full batch even when this call renders fewer frames, so that a later, longer
   // call does not reallocate gigabytes in the middle of a render (grow-only)
   rc  = ensureWavefront(ctx, (size_t)nLocal * fif);
