@@ -166,6 +166,7 @@ def main():
                          "(PREFER_FAST_TRACE, src/accelstruct.cpp:125): host binned SAH up to 2 M triangles, GPU LBVH + leaf collapse above; "
                          "0 GPU LBVH, 1 GPU LBVH + SAH leaf collapse, 2 host binned SAH, 3 GPU PLOC + SAH leaf collapse")
     ap.add_argument("--frames-in-flight", type=int, default=0)
+    ap.add_argument("--sort-rays", action="store_true", help="vkrt_render_opts.sort_rays: order each bounce's queue by octant + origin Morton key")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -219,6 +220,7 @@ def main():
     opts = S.RenderOpts()
     opts.shard_rank, opts.shard_count = (rank, world) if use_dist else (0, 1)
     opts.frames_in_flight = args.frames_in_flight
+    opts.sort_rays = 1 if args.sort_rays else 0
     opts.profile = 0    # timed region: no per-kernel events, so shadow(b) overlaps closest(b+1) on the library's second stream
 
     def barrier():
@@ -272,18 +274,20 @@ def main():
     opts_p = S.RenderOpts()
     opts_p.shard_rank, opts_p.shard_count, opts_p.profile = opts.shard_rank, opts.shard_count, 1
     opts_p.frames_in_flight = args.frames_in_flight
+    opts_p.sort_rays = opts.sort_rays
     ctx.reset_stats()
     st.frame = args.warmup
     ctx.render(st, args.steps, opts_p)
     s = ctx.stats()
     kernel_ms = dict(raygen=s.ms_raygen, trace_closest=s.ms_trace_closest, trace_shadow=s.ms_trace_shadow, shade=s.ms_shade,
-                     accumulate=s.ms_accumulate)
+                     accumulate=s.ms_accumulate, sort=s.ms_sort)
 
     # ---- roofline of the dominant kernel: instrumented re-run of the same frames (untimed) gives the visit counts
     peak, peak_src = measured_peaks()
     opts_c = S.RenderOpts()
     opts_c.shard_rank, opts_c.shard_count, opts_c.count_traversal = opts.shard_rank, opts.shard_count, 1
     opts_c.frames_in_flight = args.frames_in_flight
+    opts_c.sort_rays = opts.sort_rays
     ctx.reset_stats()
     st.frame = args.warmup
     ctx.render(st, args.steps, opts_c)

@@ -223,6 +223,12 @@ def test_batching_and_sharding_do_not_change_the_image(vk, gpu):
         gpu.render(st, 6, opts)
         imgs.append(gpu.output_read())
     assert np.array_equal(imgs[0], imgs[1]) and np.array_equal(imgs[0], imgs[2])
+    # the optional ray sort (octant + origin Morton key) only reorders the queue: same image, bit for bit
+    opts = S.RenderOpts()
+    opts.sort_rays, opts.frames_in_flight = 1, 3
+    gpu.output_clear()
+    gpu.render(st, 6, opts)
+    assert np.array_equal(imgs[0], gpu.output_read()) and gpu.stats().ms_sort >= 0.0
     total = np.zeros_like(imgs[0])
     for rank in range(3):
         opts = S.RenderOpts()
@@ -293,6 +299,45 @@ def test_full_size_properties_sponza_1080p(vk, gpu, build_mode):
     got = a[rows[0]:rows[1], :, :3]
     off = (np.abs(got - ref) > 1e-3 * (1 + np.abs(ref))).any(axis=2)
     assert off.mean() < 0.002 and per_channel_rel_l2(got[~off], ref[~off]) < IMG_TOL
+
+
+def test_full_size_properties_10m_triangles_and_helmet(vk, gpu):
+    """BASELINE.json configs[4] (10.4 M triangles, BVH in HBM, 4-wide tree) and configs[1] (single PBR mesh) at full size:
+    the three GPU builders give bit-identical hits for a million random rays (the result does not depend on the tree), and
+    a render is deterministic, finite and accounts for its rays."""
+    from vk_raytrace_b200 import scenes, structs as S
+    W, H = 1920, 1080
+    sc = scenes.instanced_stress(instances_per_axis=10)
+    rays = random_rays(1_000_000, 7, extent=6.5, centre=(0.0, 5.5, 0.0))
+    hits = []
+    for mode in (0, 1, 3):
+        vk.upload_scene(gpu, sc, W, H, build_mode=mode)
+        s = gpu.stats()
+        assert s.num_triangles > 10_000_000 and s.bvh_width == 4 and s.bvh_max_depth <= 120
+        hits.append((gpu.trace_rays(rays, True).view(np.uint32), gpu.trace_rays(rays, False).view(np.uint32)))
+    assert (hits[0][0][:, 3] != 0xffffffff).mean() > 0.01            # the probe does hit geometry
+    for h in hits[1:]:
+        assert np.array_equal(hits[0][0], h[0]) and np.array_equal(hits[0][1], h[1])
+    st = S.default_rtx_state(W, H, maxDepth=8)
+    gpu.reset_stats()
+    gpu.render(st, 2, precise=False)
+    a = gpu.output_read()
+    s1 = gpu.stats()
+    gpu.output_clear()
+    gpu.render(st, 2, precise=False)
+    assert np.array_equal(a, gpu.output_read()) and np.isfinite(a).all()
+    assert 2 * W * H <= s1.closest_rays <= 2 * W * H * 8 and s1.shadow_rays <= s1.closest_rays
+    # configs[1] stand-in
+    vk.upload_scene(gpu, scenes.helmet_standin(level=6, tex_size=512, env_size=(512, 256)), W, H, build_mode=2)
+    st = S.default_rtx_state(W, H, maxDepth=6)
+    imgs = []
+    for fif in (0, 1):
+        o = S.RenderOpts()
+        o.frames_in_flight = fif
+        gpu.output_clear()
+        gpu.render(st, 2, o, precise=False)
+        imgs.append(gpu.output_read())
+    assert np.array_equal(imgs[0], imgs[1]) and np.isfinite(imgs[0]).all() and imgs[0][..., :3].mean() > 0.01
 
 
 @pytest.mark.parametrize("pbr", [0, 1])

@@ -66,6 +66,10 @@ struct vkrt_ctx
   Light*               dLights = nullptr;
   TexDesc*             dTexDescs = nullptr;
   AlphaMat*            dAlphaMats = nullptr;
+  // ray sort (opts.sort_rays): allocated on first use, sized like the wavefront
+  uint32_t *sortKeysA = nullptr, *sortKeysB = nullptr, *sortQueueAlt = nullptr;
+  void*     sortTemp = nullptr;
+  size_t    sortTempSize = 0, sortCapacity = 0;
   std::vector<uchar4*> dTexData;
   float4*              dEnv = nullptr;
   EnvAccel*            dEnvAccel = nullptr;
@@ -137,6 +141,27 @@ static void freeWavefront(vkrt_ctx* c)
   cudaFree(w.shO); cudaFree(w.shD); cudaFree(w.shC); cudaFree(w.queueCur); cudaFree(w.queueNext); cudaFree(w.counters);
   w = Wavefront{};
   c->wfCapacity = 0;
+  cudaFree(c->sortKeysA); cudaFree(c->sortKeysB); cudaFree(c->sortQueueAlt); cudaFree(c->sortTemp);
+  c->sortKeysA = c->sortKeysB = c->sortQueueAlt = nullptr;
+  c->sortTemp = nullptr;
+  c->sortTempSize = c->sortCapacity = 0;
+}
+
+// buffers of the optional ray sort, sized like the wavefront (grow-only)
+static int ensureSortBuffers(vkrt_ctx* ctx, size_t paths)
+{
+  if(paths <= ctx->sortCapacity)
+    return VKRT_OK;
+  cudaFree(ctx->sortKeysA); cudaFree(ctx->sortKeysB); cudaFree(ctx->sortQueueAlt); cudaFree(ctx->sortTemp);
+  ctx->sortKeysA = ctx->sortKeysB = ctx->sortQueueAlt = nullptr;
+  ctx->sortTemp = nullptr;
+  ctx->sortCapacity = 0;
+  CTX_CHECK(cudaMalloc(&ctx->sortKeysA, 4 * paths)); CTX_CHECK(cudaMalloc(&ctx->sortKeysB, 4 * paths));
+  CTX_CHECK(cudaMalloc(&ctx->sortQueueAlt, 4 * paths));
+  ctx->sortTempSize = sortTempBytes((uint32_t)paths);
+  CTX_CHECK(cudaMalloc(&ctx->sortTemp, ctx->sortTempSize ? ctx->sortTempSize : 16));
+  ctx->sortCapacity = paths;
+  return VKRT_OK;
 }
 
 static cudaEvent_t getEvent(vkrt_ctx* c)
@@ -832,6 +857,8 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
   // the wavefront is sized for the full batch even when this call renders fewer frames, so that a later, longer
   // call does not reallocate gigabytes in the middle of a render (grow-only)
   rc  = ensureWavefront(ctx, (size_t)nLocal * fif);
+  if(rc == VKRT_OK && o.sort_rays)
+    rc = ensureSortBuffers(ctx, (size_t)nLocal * fif);
   fif = std::min(fif, num_frames);
   if(rc != VKRT_OK) return rc;
 
@@ -841,6 +868,7 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
     const int batch = std::min(fif, num_frames - done);
     Wavefront wf    = ctx->wf;
     wf.numPaths     = nLocal * (uint32_t)batch;
+    uint32_t* sortAlt = ctx->sortQueueAlt;  // third queue buffer of the optional ray sort (rotates with queueCur)
     FrameParams fp{};
     fp.state         = *state;
     fp.state.frame   = state->frame + done;
@@ -859,6 +887,22 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
       {
         fp.depth      = depth;
         wf.shadowSlot = (uint32_t)(depth & 1);
+        if(o.sort_rays && depth >= 1)
+        {
+          // order this bounce's queue by (direction octant, origin Morton code); the live count is read back (one host
+          // synchronisation per bounce, only in this mode).  Primary rays are coherent already.
+          uint32_t live = 0;
+          CTX_CHECK(cudaMemcpyAsync(&live, wf.counters, 4, cudaMemcpyDeviceToHost, ctx->stream));
+          CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+          if(live > 64)
+          {
+            ScopedTimer t(ctx, timing, T_SORT);
+            if(launchSortQueue(ctx->stream, ctx->view, wf.rayO, wf.rayD, wf.queueCur, sortAlt, live, ctx->sortKeysA, ctx->sortKeysB, ctx->sortTemp,
+                               ctx->sortTempSize))
+              std::swap(wf.queueCur, sortAlt);
+            ctx->stats.kernel_launches += 1 + 4;  // key kernel + the radix-sort passes of the library
+          }
+        }
         TraceLaunch L{};
         L.rayO = wf.rayO; L.rayD = wf.rayD; L.queue = wf.queueCur; L.count = wf.counters + 0; L.cursor = wf.counters + 3;
         L.hit = wf.hit; L.stats = dstats;

@@ -510,8 +510,9 @@ __global__ void emptySceneKernel(float4* nodes)
     }                                                                                                                  \
   } while(0)
 
-// 32-byte nodes.  Per-lane node gathers are bound by L1 wavefronts (one 32-byte request per lane per wavefront), so a
-// node that fits one 256-bit load halves the cost of a traversal step.  The two child boxes are stored on a 16-bit grid
+// 32-byte nodes (VKRT_NODE_FORMAT=q32, and the box encoding of the 4-wide tree): a node that fits one 256-bit load.  On an
+// L2-resident BVH it is no faster than the 64-byte node (the step is latency bound, profiles/README.md); it halves the
+// footprint of an HBM-resident one.  The two child boxes are stored on a 16-bit grid
 // G(p) = (p - gridOrigin) * gridInv laid over the root box with an 8-cell margin:
 //   word 0..2: child 0  x,y,z  (lo | hi << 16)      word 3..5: child 1      word 6,7: child references (as in the fp32 node)
 // lo is rounded down and hi up after padding by 1.0625 cells: the trace kernel evaluates the slab planes as
@@ -608,8 +609,8 @@ fail:
 // ---------------------------------------------------------------------------------------------
 // BVH4: the binary tree collapsed into 4-wide nodes, boxes on the same 16-bit grid (64 bytes per node):
 //   word 3k..3k+2: child k  x,y,z (lo | hi << 16), k = 0..3      word 12..15: child references
-// A reference is a BVH4 node index, a leaf code (kLeafBit, as in the binary tree) or kEmptyRef; empty slots carry
-// an inverted box (lo 65535, hi 0) that no ray can enter.  One traversal step tests four boxes behind two 256-bit
+// A reference is a BVH4 node index or a leaf code (kLeafBit, as in the binary tree); empty slots carry an inverted box
+// (lo 65535, hi 0) that no ray can enter and repeat the reference of child 0.  One traversal step tests four boxes behind two 256-bit
 // loads, and a ray needs about half as many dependent steps as in the binary tree.
 // Built level by level from the root: each 4-wide node starts from the two children of its binary node and
 // repeatedly opens the inner child with the largest surface area until it has four children.
@@ -684,8 +685,8 @@ __global__ void collapseWideKernel(const float4* __restrict__ nodes, uint32_t* _
     }
     else
     {
-      w[3 * k + 0] = w[3 * k + 1] = w[3 * k + 2] = 0x0000ffffu;  // lo 65535, hi 0
-      w[12 + k]    = kEmptyRef;
+      w[3 * k + 0] = w[3 * k + 1] = w[3 * k + 2] = 0x0000ffffu;  // lo 65535, hi 0: cannot be entered
+      w[12 + k]    = w[12];  // ...and if rounding at astronomic distances ever let it through, it only repeats child 0
     }
   }
   uint4* out = wide + 4ull * i;

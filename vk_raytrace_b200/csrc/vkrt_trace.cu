@@ -14,7 +14,9 @@
 //     intersects triangles together;
 //   * per-thread traversal stack in shared memory ([depth][thread]: conflict free) with
 //     a local-memory overflow;
-//   * nodes are 64 B fetched as 4 x ld.global.nc.v4, triangles 48 B as 3 x ld.global.nc.v4.
+//   * nodes are 64 B fetched as 2 x ld.global.nc.v8 (centre / half-extent boxes: the slab test is FMA-pipe work),
+//     triangles 48 B as 3 x ld.global.nc.v4; optional formats: min/max fp32 nodes, 32-byte 16-bit grid nodes, and a
+//     4-wide tree with 64-byte quantised nodes (traceKernelWide, the default above 1.5 M triangles).
 //
 // Result semantics (DESIGN.md "traversal semantics", mirrored by oracle/o_scene.h):
 // nearest Moller-Trumbore hit with t in (0, tmax), ties to the lower triangle id,
@@ -74,8 +76,8 @@ __device__ __noinline__ bool alphaTestPasses(const SceneView& sc, uint32_t triId
   return !(alphaDraw(raySeed, triId) > opacity);
 }
 
-// One 64-byte node as two 256-bit loads (sm_100 LDG.E.256): the traversal is bound by L1 wavefronts of per-lane
-// gathers, and two 32-byte requests per node cost half the tag/wavefront work of four 16-byte ones.
+// One 64-byte node as two 256-bit loads (sm_100 LDG.E.256) instead of four 128-bit ones: fewer load instructions on the
+// step's dependency chain (the kernel is bound by the latency of these fetches, profiles/README.md).
 VKRT_D void loadNode256(const float4* __restrict__ nodes, uint32_t node, float4& n0, float4& n1, float4& n2, float4& n3)
 {
   const float4* p = nodes + 4ull * node;
@@ -566,33 +568,52 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_WIDE_MINBLOCKS) traceKernelW
                 : "l"(p + 2));
           }
           if(COUNT) nNodes++;
-          const uint32_t selFx = selNx ^ 0x0022u, selFy = selNy ^ 0x0022u, selFz = selNz ^ 0x0022u;
-          float    nearT = kInfinity;
-          uint32_t nearRef = kDone;
-          bool     h[4];
-          float    tn[4];
+          // far selectors re-derived per step (volatile: three registers that would otherwise be spilled and reloaded here)
+          uint32_t selFx, selFy, selFz;
+          asm volatile("xor.b32 %0, %1, 0x22;" : "=r"(selFx) : "r"(selNx));
+          asm volatile("xor.b32 %0, %1, 0x22;" : "=r"(selFy) : "r"(selNy));
+          asm volatile("xor.b32 %0, %1, 0x22;" : "=r"(selFz) : "r"(selNz));
+          const float bT = bestT * 1.0002f;
+          float       tn[4];
+          bool        h[4];
 #pragma unroll
           for(int k = 0; k < 4; k++)
           {
             const float a = fmaxf(fmaxf(__fmaf_rn(gridPlane(w[3 * k + 0], selNx), id.x, nood.x), __fmaf_rn(gridPlane(w[3 * k + 1], selNy), id.y, nood.y)),
-                                  fmaxf(__fmaf_rn(gridPlane(w[3 * k + 2], selNz), id.z, nood.z), 0.0f));
+                                  __fmaf_rn(gridPlane(w[3 * k + 2], selNz), id.z, nood.z));
             const float b = fminf(fminf(__fmaf_rn(gridPlane(w[3 * k + 0], selFx), id.x, nood.x), __fmaf_rn(gridPlane(w[3 * k + 1], selFy), id.y, nood.y)),
-                                  fminf(__fmaf_rn(gridPlane(w[3 * k + 2], selFz), id.z, nood.z), bestT));
-            h[k]  = (a <= b * 1.0002f) && (w[12 + k] != kEmptyRef);
-            tn[k] = a;
-            if(h[k] && a < nearT)
-            {
-              nearT   = a;
-              nearRef = w[12 + k];
-            }
+                                  __fmaf_rn(gridPlane(w[3 * k + 2], selFz), id.z, nood.z));
+            // max(a, 0) <= min(b, bestT) * 1.0002  <=>  a <= x && x >= 0 with x = min(b * 1.0002, bestT * 1.0002)   (bestT >= 0)
+            const float x = fminf(b * 1.0002f, bT);
+            h[k]  = (a <= x) && (x >= 0.0f);
+            tn[k] = h[k] ? a : kInfinity;
           }
-          if(nearRef != kDone)
+          // nearest hit child (empty slots repeat child 0 behind an inverted box, so they need no test of their own)
+          const bool     s01 = tn[1] < tn[0], s23 = tn[3] < tn[2];
+          const float    t01 = s01 ? tn[1] : tn[0], t23 = s23 ? tn[3] : tn[2];
+          const uint32_t r01 = s01 ? w[13] : w[12], r23 = s23 ? w[15] : w[14];
+          const bool     sab = t23 < t01;
+          const uint32_t nearRef = sab ? r23 : r01;
+          if(fminf(t01, t23) < kInfinity)
           {
-            // enter the nearest child; the other hit children wait on the stack
+            // enter the nearest child; the other hit children go on the stack.  Fast path: the slot above the top is always
+            // written and the pointer moves only for a hit -- no branches
+            if(sp + 3 <= kStackShared)
+            {
 #pragma unroll
-            for(int k = 0; k < 4; k++)
-              if(h[k] && w[12 + k] != nearRef)
-                push(w[12 + k]);
+              for(int k = 0; k < 4; k++)
+              {
+                sstack[sp * kTraceBlock] = w[12 + k];
+                sp += (h[k] && w[12 + k] != nearRef) ? 1 : 0;
+              }
+            }
+            else
+            {
+#pragma unroll
+              for(int k = 0; k < 4; k++)
+                if(h[k] && w[12 + k] != nearRef)
+                  push(w[12 + k]);
+            }
             node = nearRef;
           }
           else
