@@ -300,7 +300,7 @@ def main():
     ach_shadow = bytes_shadow / max(kernel_ms["trace_shadow"], 1e-9) / 1e6
     traffic = None
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and args.workload == "sponza_1080p":   # the capture is of this workload's bounce-0 launch
         try:
             traffic = json.load(open(prof)).get("traceClosestKernel_dram_bytes_per_launch")
         except Exception:

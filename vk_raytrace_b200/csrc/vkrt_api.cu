@@ -826,8 +826,6 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
     return fail(ctx, VKRT_ERR_INVALID, "render: RtxState.size differs from the output image");
   if(state->maxSamples < 1 || state->maxDepth < 0)
     return fail(ctx, VKRT_ERR_INVALID, "render: bad maxSamples/maxDepth");
-  if(state->debugging_mode == VKRT_DBG_HEATMAP)
-    return fail(ctx, VKRT_ERR_INVALID, "render: the clock heat-map debug mode has no wavefront equivalent");
   cudaSetDevice(ctx->device);
 
   vkrt_render_opts o{};
@@ -835,11 +833,12 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
   const int  tile     = o.tile_size > 0 ? o.tile_size : 64;
   const int  shards   = o.shard_count > 1 ? o.shard_count : 1;
   const int  rank     = shards > 1 ? o.shard_rank : 0;
-  const bool counting = o.count_traversal != 0;
+  const bool heatmap  = state->debugging_mode == VKRT_DBG_HEATMAP;  // per-pixel traversal work instead of a clock (vkrt_shade.cu)
+  const bool counting = o.count_traversal != 0 || heatmap;
   const bool timing   = o.profile != 0;  // per-kernel CUDA-event timing
   // per-kernel timing needs the kernels one after the other; otherwise shadow(b) overlaps closest(b+1) on a second stream
   static const bool overlapEnv = []() { const char* e = getenv("VKRT_OVERLAP"); return !e || atoi(e) != 0; }();
-  const bool overlap  = overlapEnv && !timing;
+  const bool overlap  = overlapEnv && !timing && !heatmap;
   // VKRT_SHADING=precise forces the IEEE-exact shade kernel for callers that cannot pass options (the C++ tools in tests)
   static const bool envPrecise = []() { const char* e = getenv("VKRT_SHADING"); return e && !strcmp(e, "precise"); }();
   if(envPrecise) o.precise_shading = 1;
@@ -905,7 +904,7 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
         }
         TraceLaunch L{};
         L.rayO = wf.rayO; L.rayD = wf.rayD; L.queue = wf.queueCur; L.count = wf.counters + 0; L.cursor = wf.counters + 3;
-        L.hit = wf.hit; L.stats = dstats;
+        L.hit = wf.hit; L.stats = dstats; L.cost = heatmap ? wf.sum : nullptr;
         {
           ScopedTimer t(ctx, timing, T_CLOSEST);
           launchTraceClosest(ctx->stream, ctx->view, L, counting, ctx->numSMs);
@@ -922,7 +921,7 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
         TraceLaunch S{};
         S.rayO = wf.shO; S.rayD = wf.shD; S.queue = nullptr;
         S.count = wf.counters + (wf.shadowSlot ? 5 : 2); S.cursor = wf.counters + (wf.shadowSlot ? 6 : 4);
-        S.shC = wf.shC; S.rad = wf.rad; S.stats = dstats;
+        S.shC = wf.shC; S.rad = wf.rad; S.stats = dstats; S.cost = heatmap ? wf.sum : nullptr;
         if(overlap)
         {
           // the any-hit kernel of this bounce runs beside the closest-hit kernel of the next one: the tail of either

@@ -59,6 +59,7 @@ struct TraceLaunch
   const float4*   shC;
   float4*         rad;
   TraceStats*     stats;      // nullptr unless counting
+  float4*         cost;       // heat-map debug mode: per path, .w accumulates the traversal steps of its rays (counting kernels only)
 };
 int  traceBvhWidth(uint32_t numTris);  // 2 or 4: tree the trace kernels walk for a scene of this size (VKRT_BVH_WIDTH)
 int  traceNodeBytes(int bvhWidth);     // bytes per node the trace kernels fetch: 64, or 32 with VKRT_NODE_FORMAT=q32

@@ -595,8 +595,28 @@ __global__ void __launch_bounds__(256) finishSampleKernel(const __grid_constant_
   if(lum > fp.state.fireflyClampThreshold)
     radiance *= fp.state.fireflyClampThreshold / lum;
   float4 s  = wf.sum[p];
-  wf.sum[p] = f4(s.x + radiance.x, s.y + radiance.y, s.z + radiance.z, 0.f);
+  wf.sum[p] = f4(s.x + radiance.x, s.y + radiance.y, s.z + radiance.z, s.w);  // .w: heat-map cost (trace kernels)
 }
+
+// ---- heat map: shaders/common.glsl:38-62 (fade, temperature) ----------------------------------------------------------
+VKRT_D float fadeT(float low, float high, float value)
+{
+  const float mid = (low + high) * 0.5f, range = (high - low) * 0.5f;
+  const float x   = 1.0f - clampf(fabsf(mid - value) / range, 0.0f, 1.0f);
+  return smoothstepf(0.0f, 1.0f, x);
+}
+VKRT_D float3 temperature(float intensity)
+{
+  return f3(0.f, 0.f, 1.f) * fadeT(-0.25f, 0.25f, intensity) + f3(0.f, 1.f, 1.f) * fadeT(0.0f, 0.5f, intensity)
+         + f3(0.f, 1.f, 0.f) * fadeT(0.25f, 0.75f, intensity) + f3(1.f, 1.f, 0.f) * fadeT(0.5f, 1.0f, intensity)
+         + f3(1.f, 0.f, 0.f) * smoothstepf(0.75f, 1.0f, intensity);
+}
+// The reference colours a pixel by the nanoseconds its invocation took (clockRealtimeEXT around the sample loop,
+// pathtrace.comp:89,108-117).  A wavefront has no per-pixel clock; the deterministic stand-in is the traversal work of the
+// pixel's rays -- BVH nodes visited + triangles tested over all samples and bounces -- at a nominal 50 ns per step, so that the
+// reference's default range [0, 65000] covers 1300 steps.  Like a clock it is not bit-reproducible from run to run: how far a lane
+// descends speculatively while a leaf is parked depends on the other rays in its warp.
+constexpr float kHeatNsPerStep = 50.0f;
 
 // ---- accumulate: pathtrace.comp:106,122-133 (running mean, frame order) ------------------------------------
 __global__ void __launch_bounds__(256) accumulateKernel(const __grid_constant__ Wavefront wf, const __grid_constant__ FrameParams fp,
@@ -611,8 +631,14 @@ __global__ void __launch_bounds__(256) accumulateKernel(const __grid_constant__ 
   for(int f = 0; f < fp.framesInBatch; f++)
   {
     const int frame      = fp.state.frame + f;
-    float3    pixelColor = f3(wf.sum[(size_t)f * wf.numLocalPixels + lp]);
+    const float4 sum     = wf.sum[(size_t)f * wf.numLocalPixels + lp];
+    float3       pixelColor = f3(sum);
     pixelColor /= (float)fp.state.maxSamples;
+    if(fp.state.debugging_mode == VKRT_DBG_HEATMAP)
+    {
+      const float low = (float)fp.state.minHeatmap, high = (float)fp.state.maxHeatmap;
+      pixelColor      = temperature(clampf((sum.w * kHeatNsPerStep - low) / (high - low), 0.0f, 1.0f));
+    }
     if(frame > 0)
       acc = mix(acc, pixelColor, 1.0f / (float)(frame + 1));
     else

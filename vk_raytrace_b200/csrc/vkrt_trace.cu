@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
   uint32_t node = kDone, leaf = 0;
   int      sp = 0;
   bool     exhausted = false;  // warp uniform: the queue has been handed out completely
-  uint32_t nNodes = 0, nTris = 0;
+  uint32_t nNodes = 0, nTris = 0, rayBase = 0;
 
   // the overflow half of the stack sits behind real calls, so that the common path is one predicated shared-memory access
   auto push = [&](uint32_t v) {
@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
           bestT   = tmax; bestU = 0.f; bestV = 0.f; bestTri = ~0u;
           node    = 0; leaf = 0; sp = 0;
           haveRay = true;
+          rayBase = nNodes + nTris;
           if(QN)
           {
             // the ray in grid space; its origin is moved to (just before) the entry into the grid cube so that
@@ -410,6 +411,12 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
 
       if(node == kDone && leaf == 0)
       {
+        if(COUNT && L.cost && MODE != MODE_ANY_PROBE)
+        {
+          // heat-map debug mode: the work this ray cost, charged to its path (one closest and one shadow ray per path and launch)
+          const uint32_t path = (MODE == MODE_SHADOW_RESOLVE) ? __float_as_uint(L.shC[slot].w) : slot;
+          L.cost[path].w += (float)(nNodes + nTris - rayBase);
+        }
         if(MODE == MODE_CLOSEST)
           L.hit[slot] = (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(bestT, bestU, bestV, __uint_as_float(bestTri));
         else if(MODE == MODE_ANY_PROBE)
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_WIDE_MINBLOCKS) traceKernelW
   uint32_t node = kDone, leaf = 0;
   int      sp = 0;
   bool     exhausted = false;
-  uint32_t nNodes = 0, nTris = 0;
+  uint32_t nNodes = 0, nTris = 0, rayBase = 0;
 
   // the overflow half of the stack sits behind real calls, so that the common path is one predicated shared-memory access
   auto push = [&](uint32_t v) {
@@ -527,6 +534,7 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_WIDE_MINBLOCKS) traceKernelW
           bestT   = tmax; bestU = 0.f; bestV = 0.f; bestTri = ~0u;
           node    = 0; leaf = 0; sp = 0;
           haveRay = true;
+          rayBase = nNodes + nTris;
           // grid-space ray, see traceKernel<QN>
           const float3 dg = d * sc.gridInv;
           id              = f3(safeInv(dg.x), safeInv(dg.y), safeInv(dg.z));
@@ -694,6 +702,12 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_WIDE_MINBLOCKS) traceKernelW
 
       if(node == kDone && leaf == 0)
       {
+        if(COUNT && L.cost && MODE != MODE_ANY_PROBE)
+        {
+          // heat-map debug mode: the work this ray cost, charged to its path (one closest and one shadow ray per path and launch)
+          const uint32_t path = (MODE == MODE_SHADOW_RESOLVE) ? __float_as_uint(L.shC[slot].w) : slot;
+          L.cost[path].w += (float)(nNodes + nTris - rayBase);
+        }
         if(MODE == MODE_CLOSEST)
           L.hit[slot] = (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(bestT, bestU, bestV, __uint_as_float(bestTri));
         else if(MODE == MODE_ANY_PROBE)
