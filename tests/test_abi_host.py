@@ -36,9 +36,15 @@ def test_struct_sizes_match_reference_layout(vk):
     import subprocess, tempfile
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "t.c")
-        open(src, "w").write('#include "vkrt_b200.h"\nint main(void){return (int)sizeof(vkrt_stats) - 192;}\n')
+        open(src, "w").write('#include <stddef.h>\n#include <stdio.h>\n#include "vkrt_b200.h"\nint main(void){'
+                             'printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(vkrt_stats), sizeof(vkrt_render_opts), offsetof(vkrt_render_opts, precise_shading),'
+                             ' offsetof(vkrt_render_opts, profile), offsetof(vkrt_stats, node_bytes), offsetof(vkrt_stats, bvh_width), offsetof(vkrt_stats, ms_build));'
+                             'return 0;}\n')
         subprocess.check_call(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), src, "-o", os.path.join(d, "t")])
-        assert subprocess.call([os.path.join(d, "t")]) == 0
+        got = [int(x) for x in subprocess.check_output([os.path.join(d, "t")], text=True).split()]
+    want = [C.sizeof(S.Stats), C.sizeof(S.RenderOpts), S.RenderOpts.precise_shading.offset, S.RenderOpts.profile.offset,
+            S.Stats.node_bytes.offset, S.Stats.bvh_width.offset, S.Stats.ms_build.offset]
+    assert got == want and got[0] == 192, (got, want)
 
 
 def test_create_fails_loudly_without_gpu(vk):
