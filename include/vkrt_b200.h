@@ -78,7 +78,7 @@ typedef struct vkrt_stats
   double   ms_sort;
   double   ms_accumulate;
   double   ms_tonemap;
-  double   ms_build;        /* last vkrt_scene_commit (transform + LBVH build)    */
+  double   ms_build;        /* last vkrt_scene_commit: the acceleration structure only (flatten, sort, hierarchy, refit, emit, node formats; host SAH included when selected) */
   uint32_t num_triangles;   /* world-space triangles in the BVH                   */
   uint32_t num_bvh_nodes;   /* BVH2 nodes (node_bytes each as read by the trace kernels) */
   uint32_t num_instances;   /* TLAS-equivalent nodes (src/accelstruct.cpp:132)    */
