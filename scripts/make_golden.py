@@ -114,6 +114,8 @@ st = S.default_rtx_state(W, H, maxDepth=4)
 o.output_create(W, H)
 o.render(st, 4)
 imgs["tonemapped_rgba8"] = o.tonemap(tm)
+imgs["tonemapped_auto1_rgba8"] = o.tonemap(S.default_tonemapper(autoExposure=1))   # post.frag:64-70 through the mip pyramid
+imgs["tonemapped_auto3_rgba8"] = o.tonemap(S.default_tonemapper(autoExposure=3))   # post.frag:72-95 (local exposure)
 rays = np.zeros((256, 8), dtype=np.float32)
 r2 = np.random.default_rng(5)
 rays[:, :3] = r2.uniform(-0.9, 0.9, (256, 3))
