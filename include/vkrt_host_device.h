@@ -46,6 +46,10 @@ enum VkrtDebugMode {
 #define VKRT_LIGHT_POINT 1
 #define VKRT_LIGHT_SPOT 2
 
+/* Inside the reference tree the reference's own shaders/host_device.h (include guard COMMON_HOST_DEVICE, glm types) has
+ * already defined these structs: use them as they are -- same names, same bytes -- and only assert the sizes. */
+#ifndef COMMON_HOST_DEVICE
+
 #pragma pack(push, 4)
 
 /* reference shaders/host_device.h:107-115 (140 bytes) */
@@ -182,6 +186,8 @@ typedef struct InstanceData {
   int32_t  materialIndex;
   int32_t  _pad;
 } InstanceData;
+
+#endif /* !COMMON_HOST_DEVICE */
 
 VKRT_STATIC_ASSERT(sizeof(SceneCamera) == 140, "SceneCamera layout");
 VKRT_STATIC_ASSERT(sizeof(VertexAttributes) == 32, "VertexAttributes layout");

@@ -74,6 +74,7 @@ struct vkrt_ctx
   float4*              dEnv = nullptr;
   EnvAccel*            dEnvAccel = nullptr;
   BvhResult            bvh;
+  uint32_t             numLightsUploaded = 0;  // entries of dLights that hold caller data (the array itself never is empty)
   SceneView            view{};
   bool                 committed = false;
   bool                 hasEnv = false;
@@ -93,6 +94,11 @@ struct vkrt_ctx
   uint32_t* dPixelOfLocal = nullptr;
   size_t    pixCapacity = 0;
   int       shardKey[5] = {-1, -1, -1, -1, -1};  // W,H,tile,rank,count
+
+  std::vector<uint2> hostTriInfo;  // vkrt_triangle_ids: host copy of bvh.triInfo, dropped with the scene
+  // scratch of vkrt_trace_rays (grow-only)
+  void*  dProbe = nullptr;
+  size_t probeCapacity = 0;
 
   // stats
   TraceStats* dStats = nullptr;
@@ -131,6 +137,7 @@ static void freeScene(vkrt_ctx* c)
   c->dVerts = nullptr; c->dIdx = nullptr; c->dGeo = nullptr; c->dInst = nullptr; c->dInstTriOffset = nullptr;
   c->dMat = nullptr; c->dLights = nullptr; c->dTexDescs = nullptr; c->dAlphaMats = nullptr;
   c->bvh = BvhResult{};
+  c->hostTriInfo.clear();
   c->committed = false;
 }
 
@@ -288,6 +295,7 @@ int vkrt_destroy(vkrt_ctx* ctx)
   if(ctx->ownsImage) cudaFree(ctx->image);
   cudaFree(ctx->dToneF); cudaFree(ctx->dTone8); cudaFree(ctx->dMips);
   cudaFree(ctx->dStats);
+  cudaFree(ctx->dProbe);
   cudaEventDestroy(ctx->evShade); cudaEventDestroy(ctx->evShadow);
   cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
@@ -473,6 +481,7 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
     lights.push_back(Light{});
   CTX_CHECK(cudaMalloc(&ctx->dLights, sizeof(Light) * lights.size()));
   CTX_CHECK(cudaMemcpyAsync(ctx->dLights, lights.data(), sizeof(Light) * lights.size(), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->numLightsUploaded = (uint32_t)ctx->lights.size();
   std::vector<TexDesc> descs(ctx->textures.size());
   for(size_t i = 0; i < ctx->textures.size(); i++)
   {
@@ -547,6 +556,9 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
     return VKRT_ERR_CUDA;
   }
   ctx->stats.kernel_launches += 1 + (uint64_t)ctx->bvh.wideDepth;
+  // a 4-wide step pushes up to three references per level: the deepest chain must fit the 128-entry traversal stack
+  if(3 * ctx->bvh.wideDepth + 4 > 128)
+    return fail(ctx, VKRT_ERR_INVALID, "scene_commit: the 4-wide BVH is deeper than the traversal stack (128 entries)");
   cudaEventRecord(e1, ctx->stream);
   CTX_CHECK(cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
@@ -826,6 +838,9 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
     return fail(ctx, VKRT_ERR_INVALID, "render: RtxState.size differs from the output image");
   if(state->maxSamples < 1 || state->maxDepth < 0)
     return fail(ctx, VKRT_ERR_INVALID, "render: bad maxSamples/maxDepth");
+  // SceneCamera.nbLights indexes the light array on the device (pathtrace.glsl:124): it must not exceed what was uploaded
+  if(ctx->view.camera.nbLights < 0 || (uint32_t)ctx->view.camera.nbLights > ctx->numLightsUploaded)
+    return fail(ctx, VKRT_ERR_INVALID, "render: SceneCamera.nbLights exceeds the number of lights given to vkrt_scene_set_lights");
   cudaSetDevice(ctx->device);
 
   vkrt_render_opts o{};
@@ -852,9 +867,24 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
     return VKRT_OK;
   int fif = o.frames_in_flight;
   if(fif <= 0)
-    fif = (int)std::max<size_t>(1, std::min<size_t>(64, (size_t)(64u << 20) / nLocal));  // ~64 M paths (11 GB of wavefront state): amortises the latency floor of thin late bounces
-  // the wavefront is sized for the full batch even when this call renders fewer frames, so that a later, longer
-  // call does not reallocate gigabytes in the middle of a render (grow-only)
+  {
+    // automatic: ~64 M paths (11 GB of wavefront state) amortise the latency floor of thin late bounces -- but never more
+    // frames than this call renders (a single interactive frame allocates for one frame), and never more than half of
+    // the memory that is free right now (168 bytes of wavefront state per path, + 12 with the ray sort)
+    fif = (int)std::max<size_t>(1, std::min<size_t>(64, (size_t)(64u << 20) / nLocal));
+    fif = std::min(fif, num_frames);
+    size_t freeB = 0, totalB = 0;
+    if((size_t)nLocal * fif > ctx->wfCapacity && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess)
+    {
+      const size_t perPath = 10 * sizeof(float4) + 8 + (o.sort_rays ? 12 : 0);
+      const size_t fit     = (freeB / 2 + ctx->wfCapacity * perPath) / (perPath * (size_t)nLocal);
+      fif                  = (int)std::max<size_t>(1, std::min<size_t>((size_t)fif, fit));
+    }
+  }
+  // an explicit frames_in_flight is reserved in full even when this call renders fewer frames, so that a later, longer call
+  // does not reallocate gigabytes in the middle of a render (grow-only)
+  if((uint64_t)nLocal * (uint64_t)fif > 0xffffffffull)
+    return fail(ctx, VKRT_ERR_INVALID, "render: pixels x frames_in_flight exceeds 2^32 paths");
   rc  = ensureWavefront(ctx, (size_t)nLocal * fif);
   if(rc == VKRT_OK && o.sort_rays)
     rc = ensureSortBuffers(ctx, (size_t)nLocal * fif);
@@ -985,12 +1015,18 @@ int vkrt_trace_rays(vkrt_ctx* ctx, const float* rays, uint32_t n, int32_t closes
     ho[i] = make_float4(r[0], r[1], r[2], r[3]);
     hd[i] = make_float4(r[4], r[5], r[6], r[7]);
   }
-  float4 *dO = nullptr, *dD = nullptr, *dH = nullptr;
-  uint32_t* dCnt = nullptr;
-  CTX_CHECK(cudaMalloc(&dO, (size_t)n * 16));
-  CTX_CHECK(cudaMalloc(&dD, (size_t)n * 16));
-  CTX_CHECK(cudaMalloc(&dH, (size_t)n * 16));
-  CTX_CHECK(cudaMalloc(&dCnt, 8));
+  // one scratch allocation (rays, hits, counters), kept by the context and grown on demand
+  const size_t need = (size_t)n * 48 + 16;
+  if(need > ctx->probeCapacity)
+  {
+    cudaFree(ctx->dProbe);
+    ctx->dProbe = nullptr;
+    ctx->probeCapacity = 0;
+    CTX_CHECK(cudaMalloc(&ctx->dProbe, need));
+    ctx->probeCapacity = need;
+  }
+  float4 *dO = (float4*)ctx->dProbe, *dD = dO + n, *dH = dD + n;
+  uint32_t* dCnt = (uint32_t*)(dH + n);
   const uint32_t cc[2] = {n, 0u};
   cudaMemcpyAsync(dO, ho.data(), (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
   cudaMemcpyAsync(dD, hd.data(), (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
@@ -1004,7 +1040,6 @@ int vkrt_trace_rays(vkrt_ctx* ctx, const float* rays, uint32_t n, int32_t closes
   ctx->stats.kernel_launches++;
   cudaMemcpyAsync(out_hits, dH, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(dO); cudaFree(dD); cudaFree(dH); cudaFree(dCnt);
   if(e != cudaSuccess)
   {
     ctx->err = std::string("trace_rays: ") + cudaGetErrorString(e);
@@ -1018,9 +1053,13 @@ int vkrt_triangle_ids(vkrt_ctx* ctx, const uint32_t* tri_ids, uint32_t n, uint32
   if(!ctx || !tri_ids || !out_node_prim) return VKRT_ERR_INVALID;
   if(!ctx->committed) return fail(ctx, VKRT_ERR_STATE, "triangle_ids: scene not committed");
   cudaSetDevice(ctx->device);
-  std::vector<uint2> info(ctx->bvh.numTris);
-  if(!info.empty())
-    CTX_CHECK(cudaMemcpy(info.data(), ctx->bvh.triInfo, sizeof(uint2) * info.size(), cudaMemcpyDeviceToHost));
+  std::vector<uint2>& info = ctx->hostTriInfo;  // fetched once per committed scene
+  if(info.size() != ctx->bvh.numTris)
+  {
+    info.resize(ctx->bvh.numTris);
+    if(!info.empty())
+      CTX_CHECK(cudaMemcpy(info.data(), ctx->bvh.triInfo, sizeof(uint2) * info.size(), cudaMemcpyDeviceToHost));
+  }
   for(uint32_t i = 0; i < n; i++)
   {
     if(tri_ids[i] < info.size()) { out_node_prim[2 * i] = info[tri_ids[i]].x; out_node_prim[2 * i + 1] = info[tri_ids[i]].y; }

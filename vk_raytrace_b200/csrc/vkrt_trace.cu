@@ -605,8 +605,9 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_WIDE_MINBLOCKS) traceKernelW
           if(fminf(t01, t23) < kInfinity)
           {
             // enter the nearest child; the other hit children go on the stack.  Fast path: the slot above the top is always
-            // written and the pointer moves only for a hit -- no branches
-            if(sp + 3 <= kStackShared)
+            // written and the pointer moves only for a hit -- no branches.  Up to three pushes, and the store of the fourth
+            // iteration lands one slot above them: slots sp .. sp + 3 must all be inside the shared array
+            if(sp + 4 <= kStackShared)
             {
 #pragma unroll
               for(int k = 0; k < 4; k++)

@@ -10,7 +10,9 @@ class CudaRenderer : public Renderer
 {
 public:
   explicit CudaRenderer(int cudaDevice = 0) : m_cudaDevice(cudaDevice) {}
-  ~CudaRenderer() override { destroy(); }
+  // The reference's Renderer has no virtual destructor (src/renderer.h:30-48: back-ends are torn down through destroy(),
+  // src/sample_example.cpp:283-287), so this one is not an override; own the object by its concrete type.
+  ~CudaRenderer() { destroy(); }
 
   // ---- Renderer (src/renderer.h:33-43) -------------------------------------------------------------------
   void setup(const VkDevice&, const VkPhysicalDevice&, uint32_t, nvvk::ResourceAllocator*) override;

@@ -75,30 +75,24 @@ struct Doc
   std::string                        dir;
 };
 
-bool readAccessor(const Doc& d, int idx, int wantComps, std::vector<float>& out, std::string& err, uint32_t* countOut = nullptr)
+// One typed element array inside a buffer view: `count` elements of `ncomp` components of `ctype`, `wantComps` floats out per element.
+bool readElements(const Doc& d, int bufferView, size_t accOffset, int ctype, bool normalized, int ncomp, int wantComps, size_t count,
+                  bool tightlyPacked, float* out, std::string& err)
 {
-  const mj::Value& acc = d.root["accessors"][(size_t)idx];
-  if(!acc.isObject()) { err = "bad accessor index"; return false; }
-  if(acc.has("sparse")) { err = "sparse accessors are not supported"; return false; }
-  const int    ctype = acc["componentType"].integer();
-  const size_t count = (size_t)acc["count"].number();
-  const std::string& type = acc["type"].string();
-  const int    ncomp = type == "SCALAR" ? 1 : type == "VEC2" ? 2 : type == "VEC3" ? 3 : type == "VEC4" ? 4 : type == "MAT4" ? 16 : 0;
-  const bool   normalized = acc["normalized"].boolean(false);
-  const int    csize = (ctype == 5120 || ctype == 5121) ? 1 : (ctype == 5122 || ctype == 5123) ? 2 : 4;
-  if(!ncomp) { err = "unsupported accessor type " + type; return false; }
-  if(countOut) *countOut = (uint32_t)count;
-  out.assign(count * (size_t)wantComps, 0.f);
-  if(!acc.has("bufferView"))
-    return true;  // all zeros
-  const mj::Value& bv = d.root["bufferViews"][(size_t)acc["bufferView"].integer()];
-  const int    bi = bv["buffer"].integer(0);
+  const mj::Value& bv = d.root["bufferViews"][(size_t)bufferView];
+  if(!bv.isObject()) { err = "bad bufferView index"; return false; }
+  const int bi = bv["buffer"].integer(0);
   if(bi < 0 || (size_t)bi >= d.buffers.size()) { err = "bad buffer index"; return false; }
   const std::vector<uint8_t>& buf = d.buffers[(size_t)bi];
-  const size_t off    = (size_t)bv["byteOffset"].number(0) + (size_t)acc["byteOffset"].number(0);
-  size_t       stride = (size_t)bv["byteStride"].number(0);
+  const int    csize  = (ctype == 5120 || ctype == 5121) ? 1 : (ctype == 5122 || ctype == 5123) ? 2 : 4;
+  const size_t off    = (size_t)bv["byteOffset"].number(0) + accOffset;
+  size_t       stride = tightlyPacked ? 0 : (size_t)bv["byteStride"].number(0);
   if(stride == 0) stride = (size_t)ncomp * csize;
-  if(count && off + (count - 1) * stride + (size_t)ncomp * csize > buf.size()) { err = "accessor out of buffer range"; return false; }
+  if(count && (off > buf.size() || (count - 1) > (buf.size() - off) / stride || off + (count - 1) * stride + (size_t)ncomp * csize > buf.size()))
+  {
+    err = "accessor out of buffer range";
+    return false;
+  }
   for(size_t i = 0; i < count; i++)
   {
     const uint8_t* p = buf.data() + off + i * stride;
@@ -111,8 +105,8 @@ bool readAccessor(const Doc& d, int idx, int wantComps, std::vector<float>& out,
         case 5125: { uint32_t u; std::memcpy(&u, p + 4 * c, 4); v = (float)u; break; }
         case 5123: { uint16_t u; std::memcpy(&u, p + 2 * c, 2); v = normalized ? u / 65535.0f : (float)u; break; }
         case 5121: { uint8_t u = p[c]; v = normalized ? u / 255.0f : (float)u; break; }
-        case 5122: { int16_t s; std::memcpy(&s, p + 2 * c, 2); v = normalized ? std::max(s / 32767.0f, -1.0f) : (float)s; break; }
-        case 5120: { int8_t s = (int8_t)p[c]; v = normalized ? std::max(s / 127.0f, -1.0f) : (float)s; break; }
+        case 5122: { int16_t q; std::memcpy(&q, p + 2 * c, 2); v = normalized ? std::max(q / 32767.0f, -1.0f) : (float)q; break; }
+        case 5120: { int8_t q = (int8_t)p[c]; v = normalized ? std::max(q / 127.0f, -1.0f) : (float)q; break; }
         default: err = "unsupported component type"; return false;
       }
       out[i * (size_t)wantComps + c] = v;
@@ -123,19 +117,65 @@ bool readAccessor(const Doc& d, int idx, int wantComps, std::vector<float>& out,
   return true;
 }
 
+// Accessor -> floats, `wantComps` per element.  Sparse accessors (glTF 2.0 section 3.6.2.3, resolved by tinygltf before the
+// reference's importer sees the data): the base array (zeros without a bufferView) with `sparse.count` elements replaced.
+bool readAccessor(const Doc& d, int idx, int wantComps, std::vector<float>& out, std::string& err, uint32_t* countOut = nullptr)
+{
+  const mj::Value& acc = d.root["accessors"][(size_t)idx];
+  if(!acc.isObject()) { err = "bad accessor index"; return false; }
+  const int    ctype = acc["componentType"].integer();
+  const size_t count = (size_t)acc["count"].number();
+  const std::string& type = acc["type"].string();
+  const int    ncomp = type == "SCALAR" ? 1 : type == "VEC2" ? 2 : type == "VEC3" ? 3 : type == "VEC4" ? 4 : type == "MAT4" ? 16 : 0;
+  const bool   normalized = acc["normalized"].boolean(false);
+  if(!ncomp) { err = "unsupported accessor type " + type; return false; }
+  if(count > (size_t)1 << 31) { err = "accessor count too large"; return false; }
+  if(countOut) *countOut = (uint32_t)count;
+  out.assign(count * (size_t)wantComps, 0.f);
+  if(wantComps == 4 && ncomp == 3)
+    for(size_t i = 0; i < count; i++) out[i * 4 + 3] = 1.0f;
+  if(acc.has("bufferView")
+     && !readElements(d, acc["bufferView"].integer(), (size_t)acc["byteOffset"].number(0), ctype, normalized, ncomp, wantComps, count, false, out.data(), err))
+    return false;
+  if(acc.has("sparse"))
+  {
+    const mj::Value& sp = acc["sparse"];
+    const size_t     n  = (size_t)sp["count"].number(0);
+    if(n > count) { err = "sparse accessor: more replaced elements than elements"; return false; }
+    std::vector<float> where(n), vals(n * (size_t)wantComps, 0.f);
+    const int ictype = sp["indices"]["componentType"].integer();
+    if(ictype != 5121 && ictype != 5123 && ictype != 5125) { err = "sparse accessor: bad index component type"; return false; }
+    if(n > ((size_t)1 << 24) && ictype == 5125) { err = "sparse accessor: too many replaced elements"; return false; }  // indices pass through float
+    if(!readElements(d, sp["indices"]["bufferView"].integer(-1), (size_t)sp["indices"]["byteOffset"].number(0), ictype, false, 1, 1, n, true, where.data(), err))
+      return false;
+    if(!readElements(d, sp["values"]["bufferView"].integer(-1), (size_t)sp["values"]["byteOffset"].number(0), ctype, normalized, ncomp, wantComps, n, true,
+                     vals.data(), err))
+      return false;
+    for(size_t k = 0; k < n; k++)
+    {
+      const size_t i = (size_t)where[k];
+      if(i >= count) { err = "sparse accessor: index out of range"; return false; }
+      std::memcpy(&out[i * (size_t)wantComps], &vals[k * (size_t)wantComps], sizeof(float) * (size_t)wantComps);
+    }
+  }
+  return true;
+}
+
 bool readIndices(const Doc& d, int idx, std::vector<uint32_t>& out, std::string& err)
 {
   std::vector<float> tmp;  // exact for < 2^24; read integers directly instead
   const mj::Value& acc = d.root["accessors"][(size_t)idx];
   const int    ctype = acc["componentType"].integer();
   const size_t count = (size_t)acc["count"].number();
+  if(!acc.isObject() || !acc.has("bufferView") || acc.has("sparse")) { err = "index accessor without a plain bufferView"; return false; }
+  if(ctype != 5121 && ctype != 5123 && ctype != 5125) { err = "bad index component type"; return false; }
   const mj::Value& bv = d.root["bufferViews"][(size_t)acc["bufferView"].integer()];
   const int    bi = bv["buffer"].integer(0);
   if(bi < 0 || (size_t)bi >= d.buffers.size()) { err = "bad buffer index"; return false; }
   const std::vector<uint8_t>& buf = d.buffers[(size_t)bi];
   const size_t csize = ctype == 5121 ? 1 : ctype == 5123 ? 2 : 4;
   const size_t off = (size_t)bv["byteOffset"].number(0) + (size_t)acc["byteOffset"].number(0);
-  if(off + count * csize > buf.size()) { err = "index accessor out of range"; return false; }
+  if(off > buf.size() || count > (buf.size() - off) / csize) { err = "index accessor out of range"; return false; }
   out.resize(count);
   for(size_t i = 0; i < count; i++)
   {
@@ -403,14 +443,15 @@ bool loadGltf(const std::string& path, GltfSceneData& out, std::string& err)
   }
 
   // drawable nodes (importDrawableNodes): flatten the default scene
-  struct Item { int node; float world[16]; };
+  struct Item { int node; float world[16]; int depth; };
   std::vector<Item> stack;
   const mj::Value&  jnodes = d.root["nodes"];
   const int         sceneIdx = d.root["scene"].integer(0);
   const mj::Value&  roots = d.root["scenes"][(size_t)std::max(0, sceneIdx)]["nodes"];
-  for(size_t i = 0; i < roots.size(); i++) { Item it; it.node = roots[i].integer(); matIdentity(it.world); stack.push_back(it); }
+  for(size_t i = 0; i < roots.size(); i++) { Item it; it.node = roots[i].integer(); it.depth = 0; matIdentity(it.world); stack.push_back(it); }
   if(roots.size() == 0)
-    for(size_t i = 0; i < jnodes.size(); i++) { Item it; it.node = (int)i; matIdentity(it.world); stack.push_back(it); }
+    for(size_t i = 0; i < jnodes.size(); i++) { Item it; it.node = (int)i; it.depth = 0; matIdentity(it.world); stack.push_back(it); }
+  size_t visited = 0;
   std::map<std::string, uint32_t> meshCache;
   int                             defaultMat = -1;
   const mj::Value& jmeshes = d.root["meshes"];
@@ -422,6 +463,10 @@ bool loadGltf(const std::string& path, GltfSceneData& out, std::string& err)
   {
     Item it = work.back();
     work.pop_back();
+    // a valid node hierarchy is a forest: a path longer than the node count, or more visits than a generous multiple of it
+    // (instanced sub-trees), means the graph has a cycle
+    if(it.node < 0 || (size_t)it.node >= jnodes.size()) { err = "node index out of range"; return false; }
+    if((size_t)it.depth > jnodes.size() || ++visited > 64 * jnodes.size() + 1024) { err = "cyclic node hierarchy"; return false; }
     const mj::Value& jn = jnodes[(size_t)it.node];
     float local[16], world[16];
     if(jn.has("matrix")) { matIdentity(local); readVec(jn["matrix"], local, 16); }
@@ -433,7 +478,7 @@ bool loadGltf(const std::string& path, GltfSceneData& out, std::string& err)
     }
     matMul(it.world, local, world);
     const mj::Value& ch = jn["children"];
-    for(size_t i = ch.size(); i-- > 0;) { Item c; c.node = ch[i].integer(); std::memcpy(c.world, world, 64); work.push_back(c); }
+    for(size_t i = ch.size(); i-- > 0;) { Item c; c.node = ch[i].integer(); c.depth = it.depth + 1; std::memcpy(c.world, world, 64); work.push_back(c); }
 
     if(jn.has("mesh"))
     {
@@ -462,13 +507,20 @@ bool loadGltf(const std::string& path, GltfSceneData& out, std::string& err)
           else { m.indices.resize(nv); for(uint32_t i = 0; i < nv; i++) m.indices[i] = i; }
           m.indices.resize(m.indices.size() / 3 * 3);
           for(uint32_t i : m.indices) if(i >= nv) { err = "index out of range"; return false; }
-          if(at.has("TEXCOORD_0")) { if(!readAccessor(d, at["TEXCOORD_0"].integer(), 2, m.texcoords, err)) return false; }
+          // every attribute accessor of a primitive must have POSITION's count (glTF 2.0 section 3.7.2.1): the packer reads nv of each
+          auto attr = [&](const char* name, int comps, std::vector<float>& dst) -> bool {
+            uint32_t cnt = 0;
+            if(!readAccessor(d, at[name].integer(), comps, dst, err, &cnt)) return false;
+            if(cnt != nv) { err = std::string("attribute ") + name + " has a different count than POSITION"; return false; }
+            return true;
+          };
+          if(at.has("TEXCOORD_0")) { if(!attr("TEXCOORD_0", 2, m.texcoords)) return false; }
           else m.texcoords.assign((size_t)nv * 2, 0.f);
-          if(at.has("NORMAL")) { if(!readAccessor(d, at["NORMAL"].integer(), 3, m.normals, err)) return false; }
+          if(at.has("NORMAL")) { if(!attr("NORMAL", 3, m.normals)) return false; }
           else generateNormals(m);
-          if(at.has("TANGENT")) { if(!readAccessor(d, at["TANGENT"].integer(), 4, m.tangents, err)) return false; }
+          if(at.has("TANGENT")) { if(!attr("TANGENT", 4, m.tangents)) return false; }
           else generateTangents(m);
-          if(at.has("COLOR_0")) { if(!readAccessor(d, at["COLOR_0"].integer(), 4, m.colors, err)) return false; }
+          if(at.has("COLOR_0")) { if(!attr("COLOR_0", 4, m.colors)) return false; }
           else m.colors.assign((size_t)nv * 4, 1.f);
           int mat = pr["material"].integer(-1);
           if(mat < 0 || (size_t)mat >= jmats.size())

@@ -87,7 +87,7 @@ const uint16_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 
 const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
 const uint16_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 
-bool inflateRaw(const uint8_t* data, size_t n, std::vector<uint8_t>& out)
+bool inflateRaw(const uint8_t* data, size_t n, std::vector<uint8_t>& out, size_t limit)
 {
   BitReader br{data, n};
   for(;;)
@@ -100,7 +100,7 @@ bool inflateRaw(const uint8_t* data, size_t n, std::vector<uint8_t>& out)
       if(br.pos + 4 > n) return false;
       uint16_t len = (uint16_t)(data[br.pos] | (data[br.pos + 1] << 8));
       br.pos += 4;
-      if(br.pos + len > n) return false;
+      if(br.pos + len > n || out.size() + len > limit) return false;
       out.insert(out.end(), data + br.pos, data + br.pos + len);
       br.pos += len;
     }
@@ -152,7 +152,7 @@ bool inflateRaw(const uint8_t* data, size_t n, std::vector<uint8_t>& out)
       {
         int sym = lit.decode(br);
         if(sym < 0 || br.bad) return false;
-        if(sym < 256) out.push_back((uint8_t)sym);
+        if(sym < 256) { if(out.size() >= limit) return false; out.push_back((uint8_t)sym); }
         else if(sym == 256) break;
         else
         {
@@ -162,7 +162,7 @@ bool inflateRaw(const uint8_t* data, size_t n, std::vector<uint8_t>& out)
           int ds  = dist.decode(br);
           if(ds < 0 || ds >= 30) return false;
           size_t d = kDistBase[ds] + br.bits(kDistExtra[ds]);
-          if(d > out.size()) return false;
+          if(d > out.size() || out.size() + (size_t)len > limit) return false;
           size_t from = out.size() - d;
           for(int k = 0; k < len; k++) out.push_back(out[from + k]);
         }
@@ -175,6 +175,7 @@ bool inflateRaw(const uint8_t* data, size_t n, std::vector<uint8_t>& out)
   return true;
 }
 
+constexpr uint32_t kMaxImageDim = 1u << 15;  // decoders refuse anything larger before allocating
 uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 int paeth(int a, int b, int c)
 {
@@ -197,7 +198,12 @@ bool decodePng(const uint8_t* data, size_t size, ImageRGBA8& out, std::string& e
     const char*    t   = reinterpret_cast<const char*>(data + p + 4);
     const uint8_t* d   = data + p + 8;
     if(p + 12 + len > size) { err = "truncated PNG"; return false; }
-    if(!std::strncmp(t, "IHDR", 4)) { w = be32(d); h = be32(d + 4); depth = d[8]; ctype = d[9]; interlace = d[12]; }
+    if(!std::strncmp(t, "IHDR", 4))
+    {
+      if(len != 13) { err = "bad PNG IHDR length"; return false; }
+      w = be32(d); h = be32(d + 4); depth = d[8]; ctype = d[9]; interlace = d[12];
+      if(d[10] != 0 || d[11] != 0 || interlace > 1) { err = "unsupported PNG compression / filter / interlace method"; return false; }
+    }
     else if(!std::strncmp(t, "IDAT", 4)) idat.insert(idat.end(), d, d + len);
     else if(!std::strncmp(t, "PLTE", 4)) plte.assign(d, d + len);
     else if(!std::strncmp(t, "tRNS", 4)) trns.assign(d, d + len);
@@ -205,10 +211,32 @@ bool decodePng(const uint8_t* data, size_t size, ImageRGBA8& out, std::string& e
     p += 12 + len;
   }
   if(w == 0 || h == 0 || idat.size() < 6) { err = "bad PNG header"; return false; }
+  if(w > kMaxImageDim || h > kMaxImageDim) { err = "PNG larger than 32768 x 32768"; return false; }
   const int chans = (ctype == 0) ? 1 : (ctype == 2) ? 3 : (ctype == 3) ? 1 : (ctype == 4) ? 2 : (ctype == 6) ? 4 : 0;
-  if(!chans || (depth != 8 && depth != 16 && !(depth < 8 && (ctype == 0 || ctype == 3)))) { err = "unsupported PNG format"; return false; }
+  // bit depths the PNG specification allows per colour type: grey 1/2/4/8/16, palette 1/2/4/8, everything else 8/16
+  const bool depthOk = (ctype == 0) ? (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)
+                       : (ctype == 3) ? (depth == 1 || depth == 2 || depth == 4 || depth == 8)
+                                      : (depth == 8 || depth == 16);
+  if(!chans || !depthOk) { err = "unsupported PNG format"; return false; }
   std::vector<uint8_t> raw;
-  if(!inflateRaw(idat.data() + 2, idat.size() - 2, raw)) { err = "PNG inflate failed"; return false; }  // skip the zlib header
+  {
+    // the filtered size the header implies (one filter byte per row, per Adam7 pass when interlaced) must be what was inflated
+    auto passBytes = [&](uint32_t x0, uint32_t y0, uint32_t dx, uint32_t dy) -> size_t {
+      if(x0 >= w || y0 >= h) return 0;
+      const size_t pw = (w - x0 + dx - 1) / dx, ph = (h - y0 + dy - 1) / dy;
+      return ph * (1 + (pw * chans * depth + 7) / 8);
+    };
+    size_t expect = 0;
+    if(!interlace) expect = passBytes(0, 0, 1, 1);
+    else
+    {
+      static const uint32_t a7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+      for(auto& q : a7) expect += passBytes(q[0], q[1], q[2], q[3]);
+    }
+    // skip the zlib header; output beyond the expected size stops the decoder (no decompression bombs)
+    if(!inflateRaw(idat.data() + 2, idat.size() - 2, raw, expect)) { err = "PNG inflate failed"; return false; }
+    if(raw.size() != expect) { err = "PNG data size does not match its header"; return false; }
+  }
   const int bpp = std::max(1, chans * depth / 8);
   out.w = w; out.h = h;
   out.rgba.assign((size_t)w * h * 4, 255);
@@ -285,7 +313,7 @@ bool loadHdrOrPfm(const std::string& path, ImageRGBA32F& out, std::string& err)
     int w = 0, h = 0;
     std::sscanf(line().c_str(), "%d %d", &w, &h);
     const double scale = std::atof(line().c_str());
-    if(w <= 0 || h <= 0 || p + (size_t)w * h * ch * 4 > f.size()) { err = "bad PFM"; return false; }
+    if(w <= 0 || h <= 0 || w > (int)kMaxImageDim || h > (int)kMaxImageDim || p + (size_t)w * h * ch * 4 > f.size()) { err = "bad PFM"; return false; }
     out.w = w; out.h = h;
     out.rgba.resize((size_t)w * h * 4);
     for(int y = 0; y < h; y++)
@@ -318,6 +346,7 @@ bool loadHdrOrPfm(const std::string& path, ImageRGBA32F& out, std::string& err)
     char sy, sx; char ay, ax;
     if(std::sscanf(res.c_str(), "%c%c %d %c%c %d", &sy, &ay, &h, &sx, &ax, &w) != 6 || ay != 'Y' || ax != 'X') { err = "unsupported HDR orientation"; return false; }
   }
+  if(w <= 0 || h <= 0 || w > (int)kMaxImageDim || h > (int)kMaxImageDim) { err = "bad HDR dimensions"; return false; }
   out.w = w; out.h = h;
   out.rgba.resize((size_t)w * h * 4);
   std::vector<uint8_t> scan((size_t)w * 4);

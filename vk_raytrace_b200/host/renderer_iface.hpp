@@ -1,12 +1,18 @@
 // renderer_iface.hpp -- the reference's abstract back-end interface (src/renderer.h:30-48), restated so that the
 // adaptor below compiles with or without the Vulkan SDK / nvpro_core:
-//   * inside the reference tree, define VKRT_HAVE_NVPRO and include the real "renderer.h" instead;
+//   * inside the reference tree, define VKRT_HAVE_NVPRO: the real "renderer.h" (and through it the reference's
+//     shaders/host_device.h) is included instead, and include/vkrt_host_device.h then only asserts the struct sizes
+//     (tests/test_abi_host.py compiles the adaptor that way against /root/reference/src/renderer.h);
 //   * standalone (this repository, no Vulkan SDK), the Vulkan / nvvk types are opaque stand-ins of the right kind
-//     (dispatchable handles are pointers, VkExtent2D is {width,height}), so signatures and vtable shape match.
+//     (dispatchable handles are pointers, VkExtent2D is {width,height}) and the class below is the reference's declaration
+//     member for member -- no virtual destructor there, none here -- so signatures and vtable shape match.
 #pragma once
 #include <cstdint>
 #include <string>
 #include <vector>
+#ifdef VKRT_HAVE_NVPRO
+#include "renderer.h"  // src/renderer.h of the reference tree (pulls nvvk + shaders/host_device.h)
+#endif
 #include "../../include/vkrt_b200.h"
 
 #ifndef VKRT_HAVE_NVPRO
@@ -28,7 +34,6 @@ class Scene;
 class Renderer
 {
 public:
-  virtual ~Renderer() = default;
   virtual void setup(const VkDevice& device, const VkPhysicalDevice& physicalDevice, uint32_t familyIndex, nvvk::ResourceAllocator* allocator) = 0;
   virtual void destroy() = 0;
   virtual void run(const VkCommandBuffer& cmdBuf, const VkExtent2D& size, nvvk::ProfilerVK& profiler,
