@@ -45,6 +45,11 @@ def make_scene(cfg):
     return scenes.cornell_box()
 
 
+def default_build_mode(num_triangles):
+    """The builder bench.py uses when --build-mode is not given (also what tests/test_gpu_parity.py validates against the oracle)."""
+    return 2 if num_triangles <= 2_000_000 else 1
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -118,6 +123,53 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_cores():
+    """Threads the CPU arm may really use on this box: the scheduler affinity of this process, capped by the cgroup CPU quota
+    (os.cpu_count() reports the machine, not the container: round 1's CPU arm swung 5.8x between two boxes with '128 cores')."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    quota = float(txt[0]) / float(txt[1])
+            else:
+                q = float(txt[0])
+                if q > 0:
+                    quota = q / float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            break
+        except Exception:
+            continue
+    if quota:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n
+
+
+def vulkan_probe():
+    """is the reference's own Vulkan path runnable on this box?  Looked up at run time, not assumed."""
+    import glob
+    import shutil
+    icds = sorted(glob.glob("/usr/share/vulkan/icd.d/*.json") + glob.glob("/etc/vulkan/icd.d/*.json"))
+    info = shutil.which("vulkaninfo")
+    summary = None
+    if info:
+        try:
+            r = subprocess.run([info, "--summary"], capture_output=True, text=True, timeout=20)
+            summary = (r.stdout or r.stderr).strip().splitlines()[:3]
+        except Exception as e:   # noqa: BLE001
+            summary = [f"vulkaninfo failed: {e}"]
+    glslang = shutil.which("glslangValidator") or shutil.which("glslc")
+    runnable = bool(icds) and info is not None and glslang is not None
+    return {"icd_files": icds, "vulkaninfo": info, "vulkaninfo_summary": summary, "glsl_compiler": glslang,
+            "driver_capabilities": os.environ.get("NVIDIA_DRIVER_CAPABILITIES"), "reference_vulkan_runnable": runnable,
+            "note": "the reference needs a Vulkan ICD with VK_KHR_ray_query, glslang and the un-vendored nvpro_core; "
+                    + ("present" if runnable else "not all present on this box, so its RTX / ray-query paths cannot be timed here")}
+
+
 def cpu_reference(cfg, steps, warmup, threads=0, budget_s=20.0):
     """The reference has no CPU path and its Vulkan paths cannot run here; the timed CPU arm is the oracle port
     (oracle/, std::thread over scanlines) on a bounded sample of the same workload: a centred band of rows."""
@@ -125,10 +177,10 @@ def cpu_reference(cfg, steps, warmup, threads=0, budget_s=20.0):
     from oracle import binding as ob
     scene = make_scene(cfg)
     W, H = cfg["w"], cfg["h"]
-    o = ob.Oracle(threads=threads)
-    upload_scene(o, scene, W, H)
+    cores = threads or host_cores()
+    o = ob.Oracle(threads=cores)
+    upload_scene(o, scene, W, H, packer=ob)      # the oracle's own vertex packer and camera: no product code on this arm
     st = S.default_rtx_state(W, H, maxDepth=cfg["depth"])
-    cores = threads or os.cpu_count()
     # calibrate the band so that the whole run stays bounded
     rows = max(2, H // 90)
     r0 = (H - rows) // 2
@@ -169,6 +221,8 @@ def main():
     ap.add_argument("--sort-rays", action="store_true", help="vkrt_render_opts.sort_rays: order each bounce's queue by octant + origin Morton key")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-hbm-record", action="store_true", help="skip the HBM-resident roofline record (instanced_10m sub-run, N=1)")
+    ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the 3840x2160 sub-record (BASELINE.json configs[3])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -183,13 +237,15 @@ def main():
         if rank != 0:
             return
         cb, s_per_step = cpu_reference(cfg, args.steps, args.warmup)
+        vk_probe = vulkan_probe()
         line = {"impl": "reference", "metric": "Mrays/s", "value": cb["value"], "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "scene": "procedural Sponza stand-in" if cfg["scene"] == "sponza" else cfg["scene"],
                            "resolution": [W, H], "max_depth": cfg["depth"], "spp_per_step": 1,
-                           "note": "reference Vulkan RTX / ray-query paths not runnable on this box (no Vulkan ICD, glslang, nvpro_core); "
-                                   "CPU oracle port timed instead"},
+                           "vulkan": vk_probe,
+                           "note": "the reference has no CPU path; its Vulkan RTX / ray-query paths are probed above; the CPU oracle port "
+                                   "(oracle/, fed by its own packer and camera) is what is timed"},
                 "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -206,22 +262,24 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank if use_dist else 0
     torch.cuda.set_device(device)
+    dev = f"cuda:{device}"
 
     scene = make_scene(cfg)
     if args.build_mode < 0:
-        args.build_mode = 2 if scene.num_triangles() <= 2_000_000 else 1
+        args.build_mode = default_build_mode(scene.num_triangles())
     ctx = Context(device)
     upload_scene(ctx, scene, W, H, build_mode=args.build_mode)
-    # the accumulation image lives in a torch tensor so that torch.distributed can reduce it over NVLink
-    accum = torch.zeros((H, W, 4), dtype=torch.float32, device=f"cuda:{device}")
-    ctx.output_create(W, H, accum.data_ptr())
     _, integral, _ = ctx.build_env_accel(scene.env)
-    st = S.default_rtx_state(W, H, maxDepth=cfg["depth"], pbrMode=args.pbr_mode, fireflyClampThreshold=integral * 4.0)  # src/sample_example.cpp:110
-    opts = S.RenderOpts()
-    opts.shard_rank, opts.shard_count = (rank, world) if use_dist else (0, 1)
-    opts.frames_in_flight = args.frames_in_flight
-    opts.sort_rays = 1 if args.sort_rays else 0
-    opts.profile = 0    # timed region: no per-kernel events, so shadow(b) overlaps closest(b+1) on the library's second stream
+    TILE = 64
+    shard = (rank, world) if use_dist else (0, 1)
+
+    def make_opts(**kw):
+        o = S.RenderOpts()
+        o.shard_rank, o.shard_count, o.tile_size = shard[0], shard[1], TILE
+        o.sort_rays = 1 if args.sort_rays else 0
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
 
     def barrier():
         torch.cuda.synchronize()
@@ -229,131 +287,266 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up (untimed)
-    st.frame = 0
-    ctx.render(st, args.warmup, opts)
-    if use_dist:
-        dist.reduce(accum.clone(), 0)   # warm the communicator without touching the image
-    barrier()
-    ctx.reset_stats()
+    lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
-    sampler = ClockSampler(device)
-    sampler.start()
-    barrier()
-    t_wall = time.time()
-    ctx.mark(0)
-    st.frame = args.warmup
-    ctx.render(st, args.steps, opts, sync=False)
-    ctx.mark(1)
-    ms_render = ctx.elapsed_ms()
-    ms_reduce = 0.0
-    if use_dist:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        dist.reduce(accum, 0)       # disjoint tiles + zeros: the sum is an exact gather
-        e1.record()
-        torch.cuda.synchronize()
-        ms_reduce = e0.elapsed_time(e1)
-    barrier()
-    wall_ms = (time.time() - t_wall) * 1e3
-    sampler.stop_flag.set()
-    sampler.join(timeout=3)
-    s = ctx.stats()
-    my_ms = ms_render + ms_reduce
-    rays = int(s.closest_rays + s.shadow_rays)
-    if use_dist:
-        t = torch.tensor([my_ms], dtype=torch.float64, device=f"cuda:{device}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        r = torch.tensor([rays], dtype=torch.int64, device=f"cuda:{device}")
-        dist.all_reduce(r, op=dist.ReduceOp.SUM)
-        total_ms, total_rays = float(t.item()), int(r.item())
-    else:
-        total_ms, total_rays = my_ms, rays
-    launches = int(s.kernel_launches)
-    # per-kernel device time: the same frames again with per-kernel CUDA events (kernels serialised, untimed pass)
-    opts_p = S.RenderOpts()
-    opts_p.shard_rank, opts_p.shard_count, opts_p.profile = opts.shard_rank, opts.shard_count, 1
-    opts_p.frames_in_flight = args.frames_in_flight
-    opts_p.sort_rays = opts.sort_rays
-    ctx.reset_stats()
-    st.frame = args.warmup
-    ctx.render(st, args.steps, opts_p)
-    s = ctx.stats()
-    kernel_ms = dict(raygen=s.ms_raygen, trace_closest=s.ms_trace_closest, trace_shadow=s.ms_trace_shadow, shade=s.ms_shade,
-                     accumulate=s.ms_accumulate, sort=s.ms_sort)
+    class Exchange:
+        """Image exchange of a sharded render: every rank packs the pixels it owns (RGBA32F, 1/N of the image) and rank 0 gathers and
+        scatters them -- the exact image of a single-GPU render, with 1/N of the bytes of a zero-padded full-image reduce."""
 
-    # ---- roofline of the dominant kernel: instrumented re-run of the same frames (untimed) gives the visit counts
+        def __init__(self, w, h):
+            self.n = [ctx.shard_size(TILE, r, world) for r in range(world)]
+            self.cap = max(self.n)
+            self.mine = torch.zeros((self.cap, 4), dtype=torch.float32, device=dev)
+            self.all = [torch.zeros((self.cap, 4), dtype=torch.float32, device=dev) for _ in range(world)] if rank == 0 else None
+            self.bytes = self.cap * 16
+
+        def run(self):
+            # everything on the library's image stream (torch.cuda.ExternalStream): pack -> NCCL gather -> scatter, no host sync
+            with torch.cuda.stream(lib_stream):
+                ctx.pack_shard(TILE, rank, world, self.mine.data_ptr())
+                dist.gather(self.mine, self.all, dst=0)
+                if rank == 0:
+                    for r in range(1, world):               # rank 0's own pixels are already in place
+                        ctx.unpack_shard(TILE, r, world, self.all[r].data_ptr())
+
+    def measure(width, height, steps, warmup, fif):
+        """One timed region at the given resolution: `warmup` untimed frames, then `steps` frames between two stream barriers of the
+        library (CUDA events), plus the shard exchange when sharded.  Returns per-rank numbers."""
+        accum = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
+        ctx.output_create(width, height, accum.data_ptr())
+        ctx.set_camera(ctx.make_camera(scene.camera["eye"], scene.camera["center"], scene.camera["up"], scene.camera["fov"], width / height,
+                                       scene.camera.get("aperture", 0.0), 0 if scene.lights is None else len(scene.lights)))
+        st = S.default_rtx_state(width, height, maxDepth=cfg["depth"], pbrMode=args.pbr_mode, fireflyClampThreshold=integral * 4.0)  # src/sample_example.cpp:110
+        n_local = ctx.shard_size(TILE, shard[0], shard[1])
+        if fif <= 0:   # the library's automatic rule, made explicit so that the warm-up call already reserves the wavefront of the timed one
+            fif = max(1, min(64, (64 << 20) // max(n_local, 1), steps))
+        opts = make_opts(frames_in_flight=fif, profile=0)   # no per-kernel events: the second stream and the second slot overlap
+        ex = Exchange(width, height) if use_dist else None
+        st.frame = 0
+        ctx.render(st, warmup, opts)
+        if ex:
+            ex.run()
+        barrier()
+        ctx.reset_stats()
+        sampler = ClockSampler(device)
+        sampler.start()
+        barrier()
+        t_wall = time.time()
+        ctx.mark(0)
+        st.frame = warmup
+        ctx.render(st, steps, opts, sync=False)
+        ms_exchange = 0.0
+        if ex:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ctx.mark(1)                      # joins the render streams into the image stream, so e0 starts after the last kernel
+            e0.record(lib_stream)
+            ex.run()
+            e1.record(lib_stream)
+        ctx.mark(1)                          # timed region = render + exchange, CUDA events on the library's stream
+        my_ms = ctx.elapsed_ms()
+        if ex:
+            torch.cuda.synchronize()
+            ms_exchange = e0.elapsed_time(e1)
+        barrier()
+        wall_ms = (time.time() - t_wall) * 1e3
+        sampler.stop_flag.set()
+        sampler.join(timeout=3)
+        s = ctx.stats()
+        rays = int(s.closest_rays + s.shadow_rays)
+        if use_dist:
+            t = torch.tensor([my_ms, ms_exchange], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            r = torch.tensor([rays], dtype=torch.int64, device=dev)
+            dist.all_reduce(r, op=dist.ReduceOp.SUM)
+            total_ms, ms_exchange, total_rays = float(t[0].item()), float(t[1].item()), int(r.item())
+        else:
+            total_ms, total_rays = my_ms, rays
+        return dict(st=st, opts=opts, fif=fif, accum=accum, ex=ex, total_ms=total_ms, total_rays=total_rays, exchange_ms=ms_exchange,
+                    exchange_bytes=(ex.bytes if ex else 0), wall_ms=wall_ms, launches=int(s.kernel_launches), clocks=sampler.summary(),
+                    stats=s, n_local=n_local)
+
+    m = measure(W, H, args.steps, args.warmup, args.frames_in_flight)
+    st, opts, accum = m["st"], m["opts"], m["accum"]
+    s = m["stats"]
+    total_ms, total_rays = m["total_ms"], m["total_rays"]
+
+    def kernel_profile(c, state, steps, first_frame, base_opts):
+        """Per-kernel device time (the same frames again with per-kernel CUDA events: kernels serialised, untimed pass) and the
+        visit counters of an instrumented pass."""
+        op = make_opts(frames_in_flight=base_opts.frames_in_flight, profile=1)
+        c.reset_stats()
+        state.frame = first_frame
+        c.render(state, steps, op)
+        sp = c.stats()
+        oc = make_opts(frames_in_flight=base_opts.frames_in_flight, count_traversal=1)
+        c.reset_stats()
+        state.frame = first_frame
+        c.render(state, steps, oc)
+        sc = c.stats()
+        return sp, sc
+
+    sp, sc = kernel_profile(ctx, st, args.steps, args.warmup, opts)
+    kernel_ms = dict(raygen=sp.ms_raygen, trace_closest=sp.ms_trace_closest, trace_shadow=sp.ms_trace_shadow, shade=sp.ms_shade,
+                     accumulate=sp.ms_accumulate, sort=sp.ms_sort)
+    # bounce classes: primary rays are coherent, everything after the first hit is not (VERDICT r1 weak #4)
+    prim_c = m["n_local"] * args.steps
+    sec_c = int(sp.closest_rays) - prim_c
+    prim_s, sec_s = int(sp.shadow_rays_primary), int(sp.shadow_rays) - int(sp.shadow_rays_primary)
+
+    def rate(n, ms):
+        return (n / (ms * 1e-3) / 1e6) if ms > 0 else None
+
+    bounce_classes = {
+        "closest_primary": {"rays": prim_c, "ms": sp.ms_trace_closest_primary, "mrays_s": rate(prim_c, sp.ms_trace_closest_primary)},
+        "closest_secondary": {"rays": sec_c, "ms": sp.ms_trace_closest - sp.ms_trace_closest_primary,
+                              "mrays_s": rate(sec_c, sp.ms_trace_closest - sp.ms_trace_closest_primary)},
+        "shadow_from_primary_hits": {"rays": prim_s, "ms": sp.ms_trace_shadow_primary, "mrays_s": rate(prim_s, sp.ms_trace_shadow_primary)},
+        "shadow_from_secondary_hits": {"rays": sec_s, "ms": sp.ms_trace_shadow - sp.ms_trace_shadow_primary,
+                                       "mrays_s": rate(sec_s, sp.ms_trace_shadow - sp.ms_trace_shadow_primary)},
+        "what": "traversal kernels only, serialised profile pass of this rank (per-kernel CUDA events)"}
+
     peak, peak_src = measured_peaks()
-    opts_c = S.RenderOpts()
-    opts_c.shard_rank, opts_c.shard_count, opts_c.count_traversal = opts.shard_rank, opts.shard_count, 1
-    opts_c.frames_in_flight = args.frames_in_flight
-    opts_c.sort_rays = opts.sort_rays
-    ctx.reset_stats()
-    st.frame = args.warmup
-    ctx.render(st, args.steps, opts_c)
-    sc = ctx.stats()
-    c_nodes, c_tris = sc.nodes_visited - sc.shadow_nodes_visited, sc.tris_tested - sc.shadow_tris_tested
-    node_bytes = int(sc.node_bytes) or 64
-    bytes_closest = algorithmic_bytes(sc.closest_rays, c_nodes, c_tris, node_bytes)
-    bytes_shadow = algorithmic_bytes(sc.shadow_rays, sc.shadow_nodes_visited, sc.shadow_tris_tested, node_bytes)
-    ach_closest = bytes_closest / max(kernel_ms["trace_closest"], 1e-9) / 1e6   # GB/s
-    ach_shadow = bytes_shadow / max(kernel_ms["trace_shadow"], 1e-9) / 1e6
-    traffic = None
-    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(prof) and args.workload == "sponza_1080p":   # the capture is of this workload's bounce-0 launch
-        try:
-            traffic = json.load(open(prof)).get("traceClosestKernel_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
-    roofline = {"kernel": "traceKernel<CLOSEST>", "bound": "hbm", "achieved": ach_closest, "peak": peak, "unit": "GB/s", "frac": ach_closest / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "per_ray": {"node_bytes": node_bytes, "nodes": c_nodes / max(1, sc.closest_rays), "tris": c_tris / max(1, sc.closest_rays),
-                            "bytes": bytes_closest / max(1, sc.closest_rays)},
-                "shadow_kernel": {"achieved": ach_shadow, "frac": ach_shadow / peak,
-                                  "nodes_per_ray": sc.shadow_nodes_visited / max(1, sc.shadow_rays),
-                                  "tris_per_ray": sc.shadow_tris_tested / max(1, sc.shadow_rays)},
-                "note": "algorithmic bytes (SURVEY 8d) / summed CUDA-event kernel time of the serialised pass.  For L2-resident scenes "
-                        "(this one: 30 MB BVH) the algorithmic rate exceeds the HBM peak because node traffic is served by L1/L2; DRAM "
-                        "traffic (`traffic`, ncu, bounce-0 launch) is the ray / hit streams only.  What bounds the kernel is the latency of "
-                        "the dependent node fetches at 32 warps per SM (profiles/README.md); the HBM-resident case is instanced_10m."}
 
-    # ---- e2e: host buffers in, host image out, every step through the C ABI (rank-local; N=1 only)
+    def trace_record(stats_p, stats_c):
+        c_nodes, c_tris = stats_c.nodes_visited - stats_c.shadow_nodes_visited, stats_c.tris_tested - stats_c.shadow_tris_tested
+        nb = int(stats_c.node_bytes) or 64
+        bytes_c = algorithmic_bytes(stats_c.closest_rays, c_nodes, c_tris, nb)
+        bytes_s = algorithmic_bytes(stats_c.shadow_rays, stats_c.shadow_nodes_visited, stats_c.shadow_tris_tested, nb)
+        return {"achieved": bytes_c / max(stats_p.ms_trace_closest, 1e-9) / 1e6, "bytes_per_launch_set": bytes_c,
+                "per_ray": {"node_bytes": nb, "nodes": c_nodes / max(1, stats_c.closest_rays), "tris": c_tris / max(1, stats_c.closest_rays),
+                            "bytes": bytes_c / max(1, stats_c.closest_rays)},
+                "shadow_kernel": {"achieved": bytes_s / max(stats_p.ms_trace_shadow, 1e-9) / 1e6,
+                                  "nodes_per_ray": stats_c.shadow_nodes_visited / max(1, stats_c.shadow_rays),
+                                  "tris_per_ray": stats_c.shadow_tris_tested / max(1, stats_c.shadow_rays)},
+                "ms_trace_closest": stats_p.ms_trace_closest, "closest_rays": int(stats_c.closest_rays), "bvh_width": int(stats_c.bvh_width)}
+
+    def profile_traffic(key):
+        prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        try:
+            return json.load(open(prof)).get(key)
+        except Exception:
+            return None
+
+    head = trace_record(sp, sc)
+    bvh_bytes = int(s.num_bvh_nodes) * int(sc.node_bytes or 64) + int(s.num_triangles) * 48
+    l2_resident = bvh_bytes < 100e6
+    headline_kernel = {"kernel": "traceKernelWide<CLOSEST>" if head["bvh_width"] == 4 else "traceKernel<CLOSEST>", "workload": args.workload,
+                       "bound": "latency+divergence (L2-resident BVH)" if l2_resident else "hbm",
+                       "bvh_bytes": bvh_bytes, "algorithmic_gbs": head["achieved"], "per_ray": head["per_ray"], "shadow_kernel": head["shadow_kernel"],
+                       "dram_bytes_per_launch_ncu": profile_traffic(f"{args.workload}_closest_dram_bytes_per_launch"),
+                       "dram_gbs_ncu": profile_traffic(f"{args.workload}_closest_dram_gbs"),
+                       "lanes_per_instruction_ncu": profile_traffic(f"{args.workload}_closest_lanes_per_instruction"),
+                       "note": "the BVH of this workload lives in the 126 MB L2: node bytes never cross HBM, so an HBM fraction is not defined for it "
+                               "(round 1 printed 1.69).  ncu (profiles/): DRAM traffic is the ray and hit streams only; the kernel is bound by the "
+                               "latency of dependent node fetches and by SIMT divergence of incoherent rays.  `algorithmic_gbs` is SURVEY 8d's "
+                               "bytes / summed CUDA-event time, reported for continuity, not as a fraction of any peak."}
+
+    # ---- HBM-resident roofline record (the one `frac` is defined for): the 10.4 M-triangle scene, 1.2 GB of nodes + triangles,
+    #      measured in this same run for the 4-wide tree (the default above 1.5 M triangles) and the binary tree
+    roofline = None
+    if not use_dist and not args.no_hbm_record:
+        def hbm_record(width_flag, label):
+            c2 = ctx if args.workload == "instanced_10m" and width_flag == 0 else Context(device)
+            cfg2 = WORKLOADS["instanced_10m"]
+            if c2 is not ctx:
+                sc2 = make_scene(cfg2)
+                upload_scene(c2, sc2, cfg2["w"], cfg2["h"], build_mode=default_build_mode(sc2.num_triangles()) | width_flag)
+            st2 = S.default_rtx_state(cfg2["w"], cfg2["h"], maxDepth=cfg2["depth"], fireflyClampThreshold=4.0)
+            k = 8
+            o2 = make_opts(frames_in_flight=k)
+            c2.render(st2, k, o2)                         # warm-up
+            p2, n2 = kernel_profile(c2, st2, k, k, o2)
+            rec = trace_record(p2, n2)
+            tri = int(c2.stats().num_triangles)
+            nodes = int(c2.stats().num_bvh_nodes)
+            if c2 is not ctx:
+                c2.close()
+            rec.update({"tree": label, "triangles": tri, "bvh_bytes": nodes * 64 + tri * 48, "frames": k})
+            return rec
+        r4 = hbm_record(0x200, "bvh4")
+        r2 = hbm_record(0x100, "bvh2")
+        traffic = profile_traffic("instanced_10m_closest_dram_bytes_per_launch")
+        roofline = {"kernel": "traceKernelWide<CLOSEST>", "workload": "instanced_10m (HBM resident: %.2f GB of nodes + triangles)" % (r4["bvh_bytes"] / 1e9),
+                    "bound": "hbm", "achieved": r4["achieved"], "peak": peak, "unit": "GB/s", "frac": r4["achieved"] / peak,
+                    "traffic": traffic, "peak_source": peak_src, "per_ray": r4["per_ray"], "ms_trace_closest": r4["ms_trace_closest"],
+                    "closest_rays": r4["closest_rays"], "frames": r4["frames"],
+                    "bvh2": {"achieved": r2["achieved"], "frac": r2["achieved"] / peak, "per_ray": r2["per_ray"], "ms_trace_closest": r2["ms_trace_closest"]},
+                    "headline_kernel": headline_kernel,
+                    "note": "achieved = algorithmic bytes (ray 32 + hit 16 + 64 per node visited + 48 per triangle tested, visit counters of an "
+                            "instrumented pass over the same frames) / summed CUDA-event time of the closest-hit launches of those frames; both "
+                            "trees fetch 64-byte nodes.  `traffic` = ncu dram bytes of one closest-hit launch (profiles/).  The headline workload's "
+                            "BVH is L2 resident: see headline_kernel."}
+    else:
+        roofline = {"kernel": headline_kernel["kernel"], "workload": args.workload, "bound": headline_kernel["bound"], "achieved": head["achieved"],
+                    "peak": peak, "unit": "GB/s", "frac": (head["achieved"] / peak) if not l2_resident else None, "traffic": None,
+                    "peak_source": peak_src, "per_ray": head["per_ray"], "headline_kernel": headline_kernel,
+                    "note": "multi-GPU / --no-hbm-record run: the HBM-resident record is measured by the N=1 default run"}
+
+    # ---- e2e: the same metric through the C ABI as an interactive host drives it, one definition for every N: per step a host
+    #      SceneCamera goes in, ONE frame is rendered (sharded when N > 1, then exchanged), and the tonemapped RGBA8 frame comes
+    #      back to page-locked host memory on rank 0.  The read-back of frame f overlaps the rendering of frame f+1
+    #      (vkrt_tonemap_async, two staging buffers), as a display loop does.
     e2e = None
-    if not args.no_e2e and not use_dist:
+    if not args.no_e2e:
         cam = scene.camera
         tm = S.default_tonemapper()
-        out8 = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True).numpy()   # pinned host frame buffer
-        opts_e = S.RenderOpts()
+        bufs = [ctx.host_alloc((H, W, 4)), ctx.host_alloc((H, W, 4))] if rank == 0 else None
+        opts_e = make_opts()
         k = max(4, min(args.steps, 16))
-        for f in range(2):
+        ex = m["ex"]
+        nl = 0 if scene.lights is None else len(scene.lights)
+
+        def step(f):
+            camera = ctx.make_camera(cam["eye"], cam["center"], cam["up"], cam["fov"], W / H, 0.0, nl)
+            ctx.set_camera(camera)          # H2D: SceneCamera (140 B) + RtxState (48 B) travel as kernel parameters
             st.frame = f
-            ctx.render(st, 1, opts_e)
-            ctx.tonemap(tm, out8)
+            ctx.render(st, 1, opts_e, sync=False)
+            if ex:
+                ex.run()
+            if rank == 0:
+                ctx.tonemap_wait(f & 1)     # the copy that last used this staging slot (frame f-2)
+                ctx.tonemap_async(tm, bufs[f & 1], f & 1)   # D2H: the displayed RGBA8 frame
+
+        for f in range(2):
+            step(f)
+        if rank == 0:
+            ctx.tonemap_wait(0)
+            ctx.tonemap_wait(1)
         ctx.reset_stats()
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.time()
         for f in range(k):
-            camera = ctx.make_camera(cam["eye"], cam["center"], cam["up"], cam["fov"], W / H, 0.0, len(scene.lights) if scene.lights is not None else 0)
-            ctx.set_camera(camera)          # H2D: SceneCamera (140 B) + RtxState (48 B) travel as kernel parameters
-            st.frame = 2 + f
-            ctx.render(st, 1, opts_e, sync=False)
-            ctx.tonemap(tm, out8)           # D2H: the displayed RGBA8 frame
+            step(2 + f)
+        if rank == 0:
+            ctx.tonemap_wait(0)
+            ctx.tonemap_wait(1)
+        ctx.sync()
+        barrier()
         dt = time.time() - t0
         se = ctx.stats()
-        e2e = {"value": (se.closest_rays + se.shadow_rays) / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 140 + 48,
-               "d2h_bytes_per_step": W * H * 4, "steps": k, "ms_per_step": dt / k * 1e3,
-               "what": "per step: vkrt_set_camera(host SceneCamera) + vkrt_render(1 frame) + vkrt_tonemap -> pinned host RGBA8 "
-                       "(interactive use: one frame per call, so no multi-frame batching)"}
-    elif use_dist:
-        # per step host traffic is the same tiny parameter upload; the image comes back once after the reduce
-        t0 = time.time()
-        host = accum.cpu() if rank == 0 else None
-        torch.cuda.synchronize()
-        d2h_ms = (time.time() - t0) * 1e3
-        e2e = {"value": total_rays / ((total_ms + d2h_ms) * 1e-3) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 140 + 48,
-               "d2h_bytes_per_step": int(W * H * 16 / max(1, args.steps)),
-               "what": "timed region + D2H of the reduced RGBA32F image on rank 0 (amortised over the steps)"}
-        del host
+        er = int(se.closest_rays + se.shadow_rays)
+        if use_dist:
+            r = torch.tensor([er], dtype=torch.int64, device=dev)
+            dist.all_reduce(r, op=dist.ReduceOp.SUM)
+            er = int(r.item())
+        e2e = {"value": er / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 140 + 48, "d2h_bytes_per_step": W * H * 4, "steps": k,
+               "ms_per_step": dt / k * 1e3,
+               "what": "per step: vkrt_set_camera(host SceneCamera) + vkrt_render(1 frame%s) + vkrt_tonemap_async -> page-locked host RGBA8 on "
+                       "rank 0; frame f's read-back overlaps frame f+1 (two staging buffers, two wavefront slots); wall clock over %d steps "
+                       "including the final waits" % (", tile shard + gather to rank 0" if use_dist else "", k)}
+        if rank == 0:
+            for b in bufs:
+                ctx.host_free(b)
+
+    # ---- C4 of BASELINE.json: the same scene at 3840x2160, tile-sharded over the ranks, in the same run (N > 1)
+    c4 = None
+    if use_dist and cfg["scene"] == "sponza" and not args.no_c4:
+        del accum
+        m4 = measure(3840, 2160, min(args.steps, 32), 3, 0)
+        c4 = {"workload": "sponza_4k (BASELINE.json configs[3]: 3840x2160, tile-sharded, exchange of the RGBA32F accumulation buffer)",
+              "value": m4["total_rays"] / (m4["total_ms"] * 1e-3) / 1e6, "unit": "Mrays/s", "steps": min(args.steps, 32),
+              "ms_per_step": m4["total_ms"] / min(args.steps, 32), "exchange_ms": m4["exchange_ms"], "exchange_bytes_per_rank": m4["exchange_bytes"],
+              "note": "1024 spp of the config bounded to these steps; Mrays/s does not depend on the sample count"}
 
     cb = None
     if rank == 0 and not args.no_cpu_baseline and not use_dist:
@@ -368,11 +561,16 @@ def main():
                                          "ms": float(s.ms_build), "bvh_width": int(s.bvh_width), "max_depth": int(s.bvh_max_depth),
                                          "what": "vkrt_scene_commit: instance flattening + BVH build, outside the timed region (SURVEY 8d)"},
                            "resolution": [W, H], "max_depth": cfg["depth"], "spp_per_step": 1, "pbr_mode": args.pbr_mode,
-                           "sharding": f"{world} x interleaved 64x64 tiles" if use_dist else "none",
+                           "frames_in_flight": m["fif"],
+                           "sharding": f"{world} x interleaved 64x64 tiles, gather of owned pixels to rank 0" if use_dist else "none",
                            "l2": "per-step wavefront state (~170 B x %d paths) exceeds the 126 MB L2; the BVH/geometry is L2-resident by design" % (W * H),
-                           "rays_counted": "ClosestHit + AnyHit calls (device counters)"},
-                "rays": total_rays, "gpu_launches": launches, "kernel_ms": kernel_ms, "reduce_ms": ms_reduce, "wall_ms": wall_ms,
-                "clocks": sampler.summary(), "roofline": roofline, "e2e": e2e}
+                           "rays_counted": "ClosestHit + AnyHit calls (device counters)",
+                           "vulkan": vulkan_probe()},
+                "rays": total_rays, "gpu_launches": m["launches"], "kernel_ms": kernel_ms, "bounce_classes": bounce_classes,
+                "reduce_ms": m["exchange_ms"], "exchange_bytes_per_rank": m["exchange_bytes"], "wall_ms": m["wall_ms"],
+                "clocks": m["clocks"], "roofline": roofline, "e2e": e2e}
+        if c4 is not None:
+            line["c4"] = c4
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line))

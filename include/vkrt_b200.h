@@ -19,6 +19,7 @@
 #ifndef VKRT_B200_H
 #define VKRT_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 #include "vkrt_host_device.h"
 
@@ -44,6 +45,11 @@ typedef struct vkrt_ctx vkrt_ctx;
 #define VKRT_BUILD_LBVH_COLLAPSED 1 /* LBVH + bottom-up SAH leaf collapse */
 #define VKRT_BUILD_SAH_HOST 2       /* GPU flatten + host binned-SAH BVH2 (slow build, fast trace) */
 #define VKRT_BUILD_PLOC 3           /* GPU: Morton sort + parallel locally-ordered clustering + SAH leaf collapse (SAH-like quality) */
+#define VKRT_BUILD_MODE_MASK 0xff
+/* OR-ed into build_mode: which tree the traversal kernels walk for this scene, overriding the size rule
+ * (binary while the BVH fits the L2, 4-wide above 1.5 M triangles) and the VKRT_BVH_WIDTH environment switch. */
+#define VKRT_BUILD_FORCE_BVH2 0x100
+#define VKRT_BUILD_FORCE_BVH4 0x200
 
 typedef struct vkrt_render_opts
 {
@@ -89,7 +95,12 @@ typedef struct vkrt_stats
   uint32_t node_bytes;      /* bytes per node fetched by the trace kernels: 32 (16-bit grid boxes, default) or 64 (fp32) */
   uint32_t bvh_width;       /* children per node of the active traversal kernel: 2 (default) or 4 */
   uint32_t _pad;
-  double   reserved[4];
+  /* bounce classes (opts.profile = 1): device time of the depth-0 launches alone.  Primary rays are coherent, everything
+   * after the first hit is not; closest_rays at depth 0 = pixels x frames, shadow rays at depth 0 are counted here. */
+  double   ms_trace_closest_primary;
+  double   ms_trace_shadow_primary;
+  uint64_t shadow_rays_primary;
+  double   reserved[1];
 } vkrt_stats;
 
 /* ---- context ---------------------------------------------------------- */
@@ -157,6 +168,26 @@ int vkrt_output_read(vkrt_ctx* ctx, float* host_rgba32f);
 int vkrt_tonemap(vkrt_ctx* ctx, const Tonemapper* tonemapper, uint8_t* host_rgba8);
 /* Same, result left on the device as float RGBA (for tests) or RGBA8. */
 int vkrt_tonemap_float(vkrt_ctx* ctx, const Tonemapper* tonemapper, float* host_rgba32f);
+/* The display path of an interactive host (src/sample_example.cpp:417-426 renders frame f+1 while frame f is presented):
+ * tonemap the image as it is after the frames enqueued so far and copy the RGBA8 result to `host_rgba8` WITHOUT waiting --
+ * the copy overlaps the next vkrt_render.  `slot` (0 or 1) names one of two device staging buffers; the host buffer
+ * must stay valid (and should be page-locked: vkrt_host_alloc) until vkrt_tonemap_wait(ctx, slot) returns. */
+int vkrt_tonemap_async(vkrt_ctx* ctx, const Tonemapper* tonemapper, uint8_t* host_rgba8, int32_t slot);
+int vkrt_tonemap_wait(vkrt_ctx* ctx, int32_t slot);
+/* Page-locked host memory for the asynchronous read-back (cudaHostAlloc / cudaFreeHost). */
+int vkrt_host_alloc(size_t bytes, void** out_ptr);
+int vkrt_host_free(void* ptr);
+
+/* ---- tile shards (one process per GPU): compact exchange instead of a full-image reduce -------- */
+
+/* Number of pixels of the shard (tile_size, shard_rank, shard_count) as vkrt_render_opts names it: tiles are dealt
+ * round-robin, t % shard_count == shard_rank. */
+int vkrt_output_shard_size(vkrt_ctx* ctx, int32_t tile_size, int32_t shard_rank, int32_t shard_count, uint32_t* out_pixels);
+/* image -> compact: the shard's pixels (RGBA32F, shard order) into a device buffer of shard_size float4.  What a rank sends. */
+int vkrt_output_pack_shard(vkrt_ctx* ctx, int32_t tile_size, int32_t shard_rank, int32_t shard_count, void* device_compact);
+/* compact -> image: scatters a shard received from rank `shard_rank` into this context's image.  What the root does with
+ * the gathered buffers; the result is bit-identical to summing zero-padded full images. */
+int vkrt_output_unpack_shard(vkrt_ctx* ctx, int32_t tile_size, int32_t shard_rank, int32_t shard_count, const void* device_compact);
 
 /* ---- render: replaces Renderer::setPushContants + Renderer::run ---------- */
 
@@ -165,6 +196,9 @@ int vkrt_tonemap_float(vkrt_ctx* ctx, const Tonemapper* tonemapper, float* host_
  * Asynchronous on the context stream; vkrt_sync() waits. */
 int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const vkrt_render_opts* opts);
 int vkrt_sync(vkrt_ctx* ctx);
+/* The CUDA stream (cudaStream_t) the image operations of this context are ordered on: work a host enqueues there between two
+ * calls (an NCCL exchange of the accumulation buffer, a Vulkan-interop copy) needs no host synchronisation. */
+int vkrt_stream(vkrt_ctx* ctx, void** out_cuda_stream);
 
 /* ---- host-side helpers of the reference's scene path (pure functions, no GPU) ------ */
 

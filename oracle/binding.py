@@ -73,6 +73,7 @@ def load():
         L.oracle_bsdf_eval.argtypes = [i32, vp, vp]
         L.oracle_bsdf_sample.argtypes = [i32, vp, u32, vp]
         L.oracle_sun_and_sky.argtypes = [vp, vp, vp]
+        L.oracle_make_camera.argtypes = [vp, vp, vp, C.c_float, C.c_float, C.c_float, i32, vp]
     return _LIB
 
 
@@ -87,6 +88,15 @@ def pack_vertices(m):
     arrs = [np.ascontiguousarray(a, dtype=np.float32) for a in (m.positions, m.normals, m.tangents, m.texcoords, m.colors)]
     load().oracle_pack_vertices(*[_ptr(a) for a in arrs], n, _ptr(out))
     return out
+
+
+def make_camera(eye, center, up, fov, aspect, aperture=0.0, nb_lights=0):
+    """Scene::updateCamera (src/scene.cpp:629-640) restated on the oracle side (glm lookAt / perspectiveRH_ZO / inverse in float)."""
+    from vk_raytrace_b200.structs import SceneCamera
+    cam = SceneCamera()
+    e, c, u = (np.ascontiguousarray(v, dtype=np.float32) for v in (eye, center, up))
+    load().oracle_make_camera(_ptr(e), _ptr(c), _ptr(u), fov, aspect, aperture, nb_lights, C.byref(cam))
+    return cam
 
 
 def build_env_accel(env):

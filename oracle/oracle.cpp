@@ -612,6 +612,74 @@ void oracle_bsdf_sample(int32_t pbrMode, const float* in, uint32_t seed, float* 
   vec3  f = pbrMode == 0 ? DisneySample(st, V, N, L, pdf, seed) : PbrSample(st, V, N, L, pdf, seed);
   out[0] = L.x; out[1] = L.y; out[2] = L.z; out[3] = f.x; out[4] = f.y; out[5] = f.z; out[6] = pdf; out[7] = uintBitsToFloat(seed);
 }
+
+// Scene::updateCamera (src/scene.cpp:629-640): view = lookAt(eye, center, up) (nvh::CameraManipulator::getMatrix), proj =
+// glm::perspectiveRH_ZO(radians(fov), aspect, 0.001, 100000) with proj[1][1] negated, both inverted with glm::inverse; focalDist =
+// |center - eye|.  Restated in single precision like glm: matrices are column-major m[col*4+row]; the inverse is the adjugate built
+// from the six 2x2 minors of the lower and of the upper row pair, divided by the determinant.
+static void inverse4(const float* m, float* out)
+{
+  // 2x2 minors of rows 2,3 (s) and rows 0,1 (c), column pairs (0,1)(0,2)(0,3)(1,2)(1,3)(2,3)
+  auto at = [&](int col, int row) { return m[col * 4 + row]; };
+  const int pr[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+  float     lo[6], hi[6];
+  for(int k = 0; k < 6; k++)
+  {
+    lo[k] = at(pr[k][0], 2) * at(pr[k][1], 3) - at(pr[k][1], 2) * at(pr[k][0], 3);
+    hi[k] = at(pr[k][0], 0) * at(pr[k][1], 1) - at(pr[k][1], 0) * at(pr[k][0], 1);
+  }
+  const float det = hi[0] * lo[5] - hi[1] * lo[4] + hi[2] * lo[3] + hi[3] * lo[2] - hi[4] * lo[1] + hi[5] * lo[0];
+  const float r   = 1.0f / det;
+  float       adj[16];
+  // adj(col j, row i) = cofactor(row j, col i)
+  adj[0 * 4 + 0] = (at(1, 1) * lo[5] - at(2, 1) * lo[4] + at(3, 1) * lo[3]);
+  adj[1 * 4 + 0] = -(at(0, 1) * lo[5] - at(2, 1) * lo[2] + at(3, 1) * lo[1]);
+  adj[2 * 4 + 0] = (at(0, 1) * lo[4] - at(1, 1) * lo[2] + at(3, 1) * lo[0]);
+  adj[3 * 4 + 0] = -(at(0, 1) * lo[3] - at(1, 1) * lo[1] + at(2, 1) * lo[0]);
+  adj[0 * 4 + 1] = -(at(1, 0) * lo[5] - at(2, 0) * lo[4] + at(3, 0) * lo[3]);
+  adj[1 * 4 + 1] = (at(0, 0) * lo[5] - at(2, 0) * lo[2] + at(3, 0) * lo[1]);
+  adj[2 * 4 + 1] = -(at(0, 0) * lo[4] - at(1, 0) * lo[2] + at(3, 0) * lo[0]);
+  adj[3 * 4 + 1] = (at(0, 0) * lo[3] - at(1, 0) * lo[1] + at(2, 0) * lo[0]);
+  adj[0 * 4 + 2] = (at(1, 3) * hi[5] - at(2, 3) * hi[4] + at(3, 3) * hi[3]);
+  adj[1 * 4 + 2] = -(at(0, 3) * hi[5] - at(2, 3) * hi[2] + at(3, 3) * hi[1]);
+  adj[2 * 4 + 2] = (at(0, 3) * hi[4] - at(1, 3) * hi[2] + at(3, 3) * hi[0]);
+  adj[3 * 4 + 2] = -(at(0, 3) * hi[3] - at(1, 3) * hi[1] + at(2, 3) * hi[0]);
+  adj[0 * 4 + 3] = -(at(1, 2) * hi[5] - at(2, 2) * hi[4] + at(3, 2) * hi[3]);
+  adj[1 * 4 + 3] = (at(0, 2) * hi[5] - at(2, 2) * hi[2] + at(3, 2) * hi[1]);
+  adj[2 * 4 + 3] = -(at(0, 2) * hi[4] - at(1, 2) * hi[2] + at(3, 2) * hi[0]);
+  adj[3 * 4 + 3] = (at(0, 2) * hi[3] - at(1, 2) * hi[1] + at(2, 2) * hi[0]);
+  // transpose into place: out(col, row) = adj(row... ) -- adj above is indexed [col*4+row] of the cofactor matrix; the inverse is its transpose
+  for(int c = 0; c < 4; c++)
+    for(int rr = 0; rr < 4; rr++)
+      out[c * 4 + rr] = adj[rr * 4 + c] * r;
+}
+void oracle_make_camera(const float eye[3], const float center[3], const float up[3], float fovDegrees, float aspect, float aperture, int32_t nbLights,
+                        SceneCamera* out)
+{
+  const vec3 e = V3(eye[0], eye[1], eye[2]), c = V3(center[0], center[1], center[2]), u0 = V3(up[0], up[1], up[2]);
+  const vec3 f = normalize(c - e);
+  const vec3 s = normalize(cross(f, u0));
+  const vec3 u = cross(s, f);
+  // glm::lookAtRH
+  const float view[16] = {s.x, u.x, -f.x, 0.f, s.y, u.y, -f.y, 0.f, s.z, u.z, -f.z, 0.f, -dot(s, e), -dot(u, e), dot(f, e), 1.f};
+  // glm::perspectiveRH_ZO, then proj[1][1] *= -1
+  const float zn = 0.001f, zf = 100000.0f;
+  const float th = std::tan(fovDegrees * 0.01745329251994329576923690768489f / 2.0f);
+  float       proj[16] = {0};
+  proj[0 * 4 + 0] = 1.0f / (aspect * th);
+  proj[1 * 4 + 1] = -(1.0f / th);
+  proj[2 * 4 + 2] = zf / (zn - zf);
+  proj[2 * 4 + 3] = -1.0f;
+  proj[3 * 4 + 2] = -(zf * zn) / (zf - zn);
+  SceneCamera cam{};
+  inverse4(view, cam.viewInverse);
+  inverse4(proj, cam.projInverse);
+  cam.focalDist = length(c - e);
+  cam.aperture  = aperture;
+  cam.nbLights  = nbLights;
+  *out          = cam;
+}
+
 void oracle_sun_and_sky(const SunAndSky* ss, const float dir[3], float out[3])
 {
   vec3 v = sky::sun_and_sky(*ss, V3(dir[0], dir[1], dir[2]));

@@ -47,3 +47,55 @@ def triangle_soup(n, seed, double_sided=False, mirrored=False):
     s.env = scenes.constant_environment(8, 4, 1.0)
     s.camera = dict(eye=(0, 0, 6), center=(0, 0, 0), up=(0, 1, 0), fov=45.0)
     return s
+
+
+def branch_scene(kind):
+    """Cornell-box variants that reach reference branches the other scenes do not (VERDICT r1 missing #8):
+    blend        BLEND alpha material, stochastic opacity (shaders/traceray_rq.glsl:87-99, pathtrace.rahit:100-112)
+    dof          thin-lens camera, aperture 0.1 (shaders/pathtrace.glsl:366-374)
+    directional  KHR_lights_punctual directional light (pathtrace.glsl:129-146, no range / spot attenuation)
+    unlit        KHR_materials_unlit material (pathtrace.glsl:259-262)
+    hdr0         RtxState.hdrMultiplier = 0 with a punctual light: lights are always selected (pathtrace.glsl:113-119)
+    Returns (scene, RtxState keyword overrides)."""
+    sc = scenes.cornell_box(with_light=(kind in ("hdr0", "blend")))
+    kw = {}
+    if kind == "blend":
+        sc.materials["alphaMode"][5] = 2                    # tall box: BLEND
+        sc.materials["pbrBaseColorFactor"][5] = (0.6, 0.7, 0.9, 0.4)
+        sc.materials["doubleSided"][5] = 1
+        sc.materials["alphaMode"][4] = 2                    # short box: BLEND, nearly opaque, single sided
+        sc.materials["pbrBaseColorFactor"][4] = (0.9, 0.85, 0.6, 0.85)
+    elif kind == "dof":
+        sc.camera = dict(sc.camera, aperture=0.1)
+    elif kind == "directional":
+        l = np.zeros(1, dtype=S.Light)
+        d = np.array([0.25, -0.35, -1.0])
+        l["direction"] = d / np.linalg.norm(d)
+        l["color"] = (1.0, 0.95, 0.9)
+        l["intensity"] = 2.5
+        l["type"] = 0
+        l["innerConeCos"], l["outerConeCos"] = 1.0, 0.7071
+        sc.lights = l
+    elif kind == "unlit":
+        sc.materials["unlit"][4] = 1
+        sc.materials["unlit"][1] = 1
+    elif kind == "hdr0":
+        kw["hdrMultiplier"] = 0.0
+    else:
+        raise KeyError(kind)
+    return sc, kw
+
+
+def blend_probe_scene(alpha=0.3):
+    """One double-sided BLEND quad at z = 0 (no texture): a ray through it is stopped with probability alpha."""
+    s = SceneDesc(name="blend_probe")
+    s.meshes = [scenes.quad((-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0), 0)]
+    s.nodes = [(np.eye(4, dtype=np.float32), 0)]
+    m = S.default_material(1)
+    m["alphaMode"] = 2
+    m["pbrBaseColorFactor"] = (1, 1, 1, alpha)
+    m["doubleSided"] = 1
+    s.materials = m
+    s.env = scenes.constant_environment(8, 4, 1.0)
+    s.camera = dict(eye=(0, 0, 3), center=(0, 0, 0), up=(0, 1, 0), fov=45.0)
+    return s

@@ -185,6 +185,42 @@ class Context:
         self._ck(self.lib.vkrt_tonemap(self.h, C.byref(tm), _ptr(out)), "tonemap")
         return out
 
+    def tonemap_async(self, tm, out, slot):
+        """vkrt_tonemap_async: tonemap + read-back into `out` (page-locked RGBA8 array) without waiting; `tonemap_wait(slot)` completes it."""
+        self._ck(self.lib.vkrt_tonemap_async(self.h, C.byref(tm), _ptr(out), slot), "tonemap_async")
+
+    def tonemap_wait(self, slot):
+        self._ck(self.lib.vkrt_tonemap_wait(self.h, slot), "tonemap_wait")
+
+    def host_alloc(self, shape, dtype=np.uint8):
+        """Page-locked host array (vkrt_host_alloc); freed with host_free(array)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        if self.lib.vkrt_host_alloc(n, C.byref(p)) != 0:
+            raise MemoryError("vkrt_host_alloc")
+        buf = (C.c_uint8 * n).from_address(p.value)
+        a = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[a.ctypes.data] = p.value
+        return a
+
+    def host_free(self, a):
+        p = getattr(self, "_pinned", {}).pop(a.ctypes.data, None)
+        if p is not None:
+            self.lib.vkrt_host_free(C.c_void_p(p))
+
+    # ---- tile shards ----
+    def shard_size(self, tile, rank, count):
+        n = C.c_uint32()
+        self._ck(self.lib.vkrt_output_shard_size(self.h, tile, rank, count, C.byref(n)), "output_shard_size")
+        return n.value
+
+    def pack_shard(self, tile, rank, count, device_ptr):
+        self._ck(self.lib.vkrt_output_pack_shard(self.h, tile, rank, count, device_ptr), "output_pack_shard")
+
+    def unpack_shard(self, tile, rank, count, device_ptr):
+        self._ck(self.lib.vkrt_output_unpack_shard(self.h, tile, rank, count, device_ptr), "output_unpack_shard")
+
     def tonemap_float(self, tm):
         out = np.empty((self.height, self.width, 4), dtype=np.float32)
         self._ck(self.lib.vkrt_tonemap_float(self.h, C.byref(tm), _ptr(out)), "tonemap_float")
@@ -205,6 +241,12 @@ class Context:
         self._ck(self.lib.vkrt_render(self.h, C.byref(state), num_frames, None if opts is None else C.byref(opts)), "render")
         if sync:
             self.sync()
+
+    def stream(self):
+        """cudaStream_t (integer handle) of the context's image-operation stream (vkrt_stream)."""
+        p = C.c_void_p()
+        self._ck(self.lib.vkrt_stream(self.h, C.byref(p)), "stream")
+        return p.value or 0
 
     def sync(self):
         self._ck(self.lib.vkrt_sync(self.h), "sync")

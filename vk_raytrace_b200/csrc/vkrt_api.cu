@@ -17,7 +17,7 @@
 using namespace vkrt;
 
 namespace vkrt {
-void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats);
+void launchShardCopy(cudaStream_t s, float4* image, const uint32_t* pixels, uint32_t n, float4* compact, bool toImage);
 }
 
 struct HostMesh
@@ -38,14 +38,30 @@ struct HostTexture
   int32_t              linear, wrapS, wrapT;
 };
 
-enum TimerSlot { T_RAYGEN = 0, T_CLOSEST, T_SHADOW, T_SHADE, T_SORT, T_ACCUM, T_TONEMAP, T_COUNT };
+enum TimerSlot { T_RAYGEN = 0, T_CLOSEST, T_SHADOW, T_SHADE, T_SORT, T_ACCUM, T_TONEMAP, T_CLOSEST0, T_SHADOW0, T_COUNT };
+
+// One wavefront in flight: its path state, its two streams (closest-hit / shade, and the any-hit kernels that overlap the next
+// bounce) and the events that order them.  A context owns two: consecutive batches -- the halves of a multi-frame render, or
+// consecutive one-frame calls of an interactive host -- alternate between them, so that the tail of every persistent kernel of
+// one wavefront is filled by kernels of the other (round 1 measured one frame per call at half the batched rate: 16 tails).
+struct WfSlot
+{
+  Wavefront    wf{};
+  size_t       capacity = 0;  // paths
+  cudaStream_t s = nullptr, s2 = nullptr;
+  cudaEvent_t  evShade = nullptr, evShadow = nullptr, evJoin = nullptr, evJoin2 = nullptr;
+};
 
 struct vkrt_ctx
 {
   int          device = 0;
-  cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // any-hit kernels, overlapped with the next bounce's closest-hit kernel
-  cudaEvent_t  evShade = nullptr, evShadow = nullptr;
+  cudaStream_t stream = nullptr;   // == slots[0].s: scene upload, image operations of the synchronous entry points, marks
+  cudaStream_t post = nullptr;     // asynchronous tonemap + read-back
+  WfSlot       slots[2];
+  uint32_t     nextSlot = 0;       // batches alternate between the slots, across calls too
+  cudaEvent_t  evImage = nullptr;  // last operation that touched the accumulation image (accumulate, clear, tonemap, read)
+  bool         imagePending = false;
+  cudaEvent_t  evFork = nullptr;
   int          numSMs = 148;
   std::string  err;
 
@@ -85,15 +101,17 @@ struct vkrt_ctx
   int     W = 0, H = 0;
   float4* dToneF = nullptr;
   uchar4* dTone8 = nullptr;
+  uchar4* dTone8Async[2] = {nullptr, nullptr};  // staging of vkrt_tonemap_async
+  cudaEvent_t evCopy[2] = {nullptr, nullptr};
+  bool    copyPending[2] = {false, false};
   float4* dMips = nullptr;  // auto-exposure mip pyramid (levels 1..n)
   size_t  mipCapacity = 0;
 
-  // wavefront
-  Wavefront wf{};
-  size_t    wfCapacity = 0;   // paths
-  uint32_t* dPixelOfLocal = nullptr;
-  size_t    pixCapacity = 0;
-  int       shardKey[5] = {-1, -1, -1, -1, -1};  // W,H,tile,rank,count
+  // pixel lists of tile shards (device), keyed by {W, H, tile, rank, count}; [0] is the one the renderer uses
+  struct ShardList { int key[5]; uint32_t* d; uint32_t n; };
+  std::vector<ShardList> shardLists;
+  uint32_t* dPixelOfLocal = nullptr;   // == the active list
+  uint32_t  numLocalPixels = 0;
 
   std::vector<uint2> hostTriInfo;  // vkrt_triangle_ids: host copy of bvh.triInfo, dropped with the scene
   // scratch of vkrt_trace_rays (grow-only)
@@ -127,6 +145,60 @@ static int fail(vkrt_ctx* ctx, int code, const char* msg)
   return code;
 }
 
+// every stream of the context idle (scene changes, statistics, teardown)
+static cudaError_t syncAll(vkrt_ctx* c)
+{
+  cudaError_t first = cudaSuccess;
+  for(auto& sl : c->slots)
+    for(cudaStream_t st : {sl.s, sl.s2})
+      if(st)
+      {
+        cudaError_t e = cudaStreamSynchronize(st);
+        if(first == cudaSuccess) first = e;
+      }
+  if(c->post)
+  {
+    cudaError_t e = cudaStreamSynchronize(c->post);
+    if(first == cudaSuccess) first = e;
+  }
+  return first;
+}
+// Image operations (accumulate, clear, tonemap, read) are enqueued in host order on different streams; each waits for the
+// previous one and leaves its own completion in evImage.
+static cudaError_t imageBegin(vkrt_ctx* c, cudaStream_t st)
+{
+  return c->imagePending ? cudaStreamWaitEvent(st, c->evImage, 0) : cudaSuccess;
+}
+static cudaError_t imageEnd(vkrt_ctx* c, cudaStream_t st)
+{
+  c->imagePending = true;
+  return cudaEventRecord(c->evImage, st);
+}
+// stream `st` waits for everything enqueued so far on all the other streams, and they wait for it: a barrier in stream order
+static cudaError_t barrierOn(vkrt_ctx* c, cudaStream_t st)
+{
+  cudaError_t first = cudaSuccess;
+  auto ck = [&](cudaError_t e) { if(first == cudaSuccess) first = e; };
+  for(auto& sl : c->slots)
+  {
+    if(sl.s && sl.s != st) { ck(cudaEventRecord(sl.evJoin, sl.s)); ck(cudaStreamWaitEvent(st, sl.evJoin, 0)); }
+    if(sl.s2) { ck(cudaEventRecord(sl.evJoin2, sl.s2)); ck(cudaStreamWaitEvent(st, sl.evJoin2, 0)); }
+  }
+  return first;
+}
+static cudaError_t forkFrom(vkrt_ctx* c, cudaStream_t st)
+{
+  cudaError_t first = cudaEventRecord(c->evFork, st);
+  for(auto& sl : c->slots)
+    for(cudaStream_t o : {sl.s, sl.s2})
+      if(o && o != st)
+      {
+        cudaError_t e = cudaStreamWaitEvent(o, c->evFork, 0);
+        if(first == cudaSuccess) first = e;
+      }
+  return first;
+}
+
 static void freeScene(vkrt_ctx* c)
 {
   cudaFree(c->dVerts); cudaFree(c->dIdx); cudaFree(c->dGeo); cudaFree(c->dInst); cudaFree(c->dInstTriOffset);
@@ -141,13 +213,17 @@ static void freeScene(vkrt_ctx* c)
   c->committed = false;
 }
 
-static void freeWavefront(vkrt_ctx* c)
+static void freeSlot(WfSlot& sl)
 {
-  Wavefront& w = c->wf;
+  Wavefront& w = sl.wf;
   cudaFree(w.rayO); cudaFree(w.rayD); cudaFree(w.hit); cudaFree(w.thr); cudaFree(w.rad); cudaFree(w.absb); cudaFree(w.sum);
   cudaFree(w.shO); cudaFree(w.shD); cudaFree(w.shC); cudaFree(w.queueCur); cudaFree(w.queueNext); cudaFree(w.counters);
-  w = Wavefront{};
-  c->wfCapacity = 0;
+  w           = Wavefront{};
+  sl.capacity = 0;
+}
+static void freeWavefront(vkrt_ctx* c)
+{
+  for(auto& sl : c->slots) freeSlot(sl);
   cudaFree(c->sortKeysA); cudaFree(c->sortKeysB); cudaFree(c->sortQueueAlt); cudaFree(c->sortTemp);
   c->sortKeysA = c->sortKeysB = c->sortQueueAlt = nullptr;
   c->sortTemp = nullptr;
@@ -206,6 +282,8 @@ static void drainTimers(vkrt_ctx* c)
   c->stats.ms_sort += acc[T_SORT];
   c->stats.ms_accumulate += acc[T_ACCUM];
   c->stats.ms_tonemap += acc[T_TONEMAP];
+  c->stats.ms_trace_closest_primary += acc[T_CLOSEST0];
+  c->stats.ms_trace_shadow_primary += acc[T_SHADOW0];
 }
 
 struct ScopedTimer
@@ -251,14 +329,23 @@ int vkrt_create(int cuda_device, vkrt_ctx** out_ctx)
     return VKRT_ERR_INVALID;
   vkrt_ctx* ctx = new vkrt_ctx();
   ctx->device   = cuda_device;
-  if(cudaSetDevice(cuda_device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+  bool ok = cudaSetDevice(cuda_device) == cudaSuccess;
+  for(auto& sl : ctx->slots)
   {
-    delete ctx;
+    ok = ok && cudaStreamCreateWithFlags(&sl.s, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&sl.s2, cudaStreamNonBlocking) == cudaSuccess;
+    for(cudaEvent_t* e : {&sl.evShade, &sl.evShadow, &sl.evJoin, &sl.evJoin2})
+      ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+  }
+  ok = ok && cudaStreamCreateWithFlags(&ctx->post, cudaStreamNonBlocking) == cudaSuccess;
+  for(cudaEvent_t* e : {&ctx->evImage, &ctx->evFork, &ctx->evCopy[0], &ctx->evCopy[1]})
+    ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+  if(!ok)
+  {
+    delete ctx;  // the process is about to report the failure; the few handles created so far go with it
     return VKRT_ERR_CUDA;
   }
-  cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
-  cudaEventCreateWithFlags(&ctx->evShade, cudaEventDisableTiming);
-  cudaEventCreateWithFlags(&ctx->evShadow, cudaEventDisableTiming);
+  ctx->stream = ctx->slots[0].s;
   cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, cuda_device);
   if(cudaMalloc(&ctx->dStats, sizeof(TraceStats)) != cudaSuccess)
   {
@@ -284,21 +371,26 @@ int vkrt_destroy(vkrt_ctx* ctx)
   if(!ctx)
     return VKRT_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  syncAll(ctx);
   drainTimers(ctx);
   for(auto e : ctx->eventPool) cudaEventDestroy(e);
   for(auto e : ctx->marks) if(e) cudaEventDestroy(e);
   freeScene(ctx);
   freeWavefront(ctx);
   cudaFree(ctx->dEnv); cudaFree(ctx->dEnvAccel);
-  cudaFree(ctx->dPixelOfLocal);
+  for(auto& l : ctx->shardLists) cudaFree(l.d);
   if(ctx->ownsImage) cudaFree(ctx->image);
-  cudaFree(ctx->dToneF); cudaFree(ctx->dTone8); cudaFree(ctx->dMips);
+  cudaFree(ctx->dToneF); cudaFree(ctx->dTone8); cudaFree(ctx->dTone8Async[0]); cudaFree(ctx->dTone8Async[1]); cudaFree(ctx->dMips);
   cudaFree(ctx->dStats);
   cudaFree(ctx->dProbe);
-  cudaEventDestroy(ctx->evShade); cudaEventDestroy(ctx->evShadow);
-  cudaStreamDestroy(ctx->stream2);
-  cudaStreamDestroy(ctx->stream);
+  for(auto& sl : ctx->slots)
+  {
+    for(cudaEvent_t e : {sl.evShade, sl.evShadow, sl.evJoin, sl.evJoin2}) cudaEventDestroy(e);
+    cudaStreamDestroy(sl.s2);
+    cudaStreamDestroy(sl.s);
+  }
+  for(cudaEvent_t e : {ctx->evImage, ctx->evFork, ctx->evCopy[0], ctx->evCopy[1]}) cudaEventDestroy(e);
+  cudaStreamDestroy(ctx->post);
   delete ctx;
   return VKRT_OK;
 }
@@ -308,7 +400,7 @@ int vkrt_scene_begin(vkrt_ctx* ctx)
 {
   if(!ctx) return VKRT_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  syncAll(ctx);
   freeScene(ctx);
   ctx->meshes.clear(); ctx->nodes.clear(); ctx->materials.clear(); ctx->lights.clear(); ctx->textures.clear();
   return VKRT_OK;
@@ -376,10 +468,15 @@ int vkrt_scene_add_texture(vkrt_ctx* ctx, const uint8_t* rgba8, uint32_t width, 
 
 int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
 {
-  if(ctx && (build_mode < VKRT_BUILD_LBVH || build_mode > VKRT_BUILD_PLOC))
-    return fail(ctx, VKRT_ERR_INVALID, "scene_commit: unknown build mode");
   if(!ctx) return VKRT_ERR_INVALID;
+  const int32_t widthFlags = build_mode & (VKRT_BUILD_FORCE_BVH2 | VKRT_BUILD_FORCE_BVH4);
+  if((build_mode & ~(VKRT_BUILD_MODE_MASK | VKRT_BUILD_FORCE_BVH2 | VKRT_BUILD_FORCE_BVH4)) || widthFlags == (VKRT_BUILD_FORCE_BVH2 | VKRT_BUILD_FORCE_BVH4))
+    return fail(ctx, VKRT_ERR_INVALID, "scene_commit: unknown build flags");
+  build_mode &= VKRT_BUILD_MODE_MASK;
+  if(build_mode < VKRT_BUILD_LBVH || build_mode > VKRT_BUILD_PLOC)
+    return fail(ctx, VKRT_ERR_INVALID, "scene_commit: unknown build mode");
   cudaSetDevice(ctx->device);
+  syncAll(ctx);
   if(ctx->materials.empty())
     return fail(ctx, VKRT_ERR_STATE, "scene_commit: no materials (the importer always appends a default one)");
   for(auto& m : ctx->meshes)
@@ -568,7 +665,7 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
   ctx->stats.ms_build       = ms;
   ctx->stats.num_triangles  = (uint32_t)totalTris;
   ctx->stats.num_bvh_nodes  = ctx->bvh.numNodes;
-  const int width           = traceBvhWidth((uint32_t)totalTris);
+  const int width           = widthFlags == VKRT_BUILD_FORCE_BVH2 ? 2 : (widthFlags == VKRT_BUILD_FORCE_BVH4 ? 4 : traceBvhWidth((uint32_t)totalTris));
   ctx->stats.node_bytes     = (uint32_t)traceNodeBytes(width);
   ctx->stats.bvh_width      = (uint32_t)width;
   if(width == 4)
@@ -593,7 +690,9 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
       attr.accessPolicyWindow.hitRatio  = (float)std::min(1.0, (double)want / (double)attr.accessPolicyWindow.num_bytes);
       attr.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
       attr.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
-      cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+      for(auto& sl : ctx->slots)
+        for(cudaStream_t st : {sl.s, sl.s2})
+          cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
       cudaGetLastError();
     }
   }
@@ -633,7 +732,7 @@ int vkrt_set_environment(vkrt_ctx* ctx, const float* rgba32f, uint32_t width, ui
 {
   if(!ctx || !rgba32f || width == 0 || height == 0) return VKRT_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  syncAll(ctx);
   cudaFree(ctx->dEnv); cudaFree(ctx->dEnvAccel);
   ctx->dEnv = nullptr; ctx->dEnvAccel = nullptr;
   const size_t n = (size_t)width * height;
@@ -676,10 +775,12 @@ int vkrt_output_create(vkrt_ctx* ctx, uint32_t width, uint32_t height, void* dev
 {
   if(!ctx || width == 0 || height == 0) return VKRT_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  syncAll(ctx);
+  ctx->imagePending = false;
+  ctx->copyPending[0] = ctx->copyPending[1] = false;
   if(ctx->ownsImage) cudaFree(ctx->image);
-  cudaFree(ctx->dToneF); cudaFree(ctx->dTone8);
-  ctx->image = nullptr; ctx->dToneF = nullptr; ctx->dTone8 = nullptr;
+  cudaFree(ctx->dToneF); cudaFree(ctx->dTone8); cudaFree(ctx->dTone8Async[0]); cudaFree(ctx->dTone8Async[1]);
+  ctx->image = nullptr; ctx->dToneF = nullptr; ctx->dTone8 = nullptr; ctx->dTone8Async[0] = ctx->dTone8Async[1] = nullptr;
   ctx->W = (int)width; ctx->H = (int)height;
   if(device_rgba32f)
   {
@@ -690,6 +791,7 @@ int vkrt_output_create(vkrt_ctx* ctx, uint32_t width, uint32_t height, void* dev
   {
     CTX_CHECK(cudaMalloc(&ctx->image, (size_t)width * height * sizeof(float4)));
     CTX_CHECK(cudaMemsetAsync(ctx->image, 0, (size_t)width * height * sizeof(float4), ctx->stream));
+    CTX_CHECK(imageEnd(ctx, ctx->stream));
     ctx->ownsImage = true;
   }
   return VKRT_OK;
@@ -706,7 +808,9 @@ int vkrt_output_clear(vkrt_ctx* ctx)
 {
   if(!ctx || !ctx->image) return VKRT_ERR_STATE;
   cudaSetDevice(ctx->device);
+  CTX_CHECK(imageBegin(ctx, ctx->stream));
   CTX_CHECK(cudaMemsetAsync(ctx->image, 0, (size_t)ctx->W * ctx->H * sizeof(float4), ctx->stream));
+  CTX_CHECK(imageEnd(ctx, ctx->stream));
   return VKRT_OK;
 }
 
@@ -714,16 +818,16 @@ int vkrt_output_read(vkrt_ctx* ctx, float* host)
 {
   if(!ctx || !ctx->image || !host) return VKRT_ERR_STATE;
   cudaSetDevice(ctx->device);
+  CTX_CHECK(imageBegin(ctx, ctx->stream));
   CTX_CHECK(cudaMemcpyAsync(host, ctx->image, (size_t)ctx->W * ctx->H * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CTX_CHECK(imageEnd(ctx, ctx->stream));
   CTX_CHECK(cudaStreamSynchronize(ctx->stream));
   return VKRT_OK;
 }
 
-static int tonemapCommon(vkrt_ctx* ctx, const Tonemapper* tm, float* hostF, uint8_t* host8)
+// Mip pyramid + tonemap kernel on `st` (the image must already be ordered before `st`): out into dF / d8.
+static int enqueueTonemap(vkrt_ctx* ctx, cudaStream_t st, const Tonemapper* tm, float4* dF, uchar4* d8, bool timed)
 {
-  if(!ctx || !tm || !ctx->image) return VKRT_ERR_STATE;
-  cudaSetDevice(ctx->device);
-  const size_t n = (size_t)ctx->W * ctx->H;
   MipView mips{};
   if(tm->autoExposure & 1)
   {
@@ -735,6 +839,7 @@ static int tonemapCommon(vkrt_ctx* ctx, const Tonemapper* tm, float* hostF, uint
       return fail(ctx, VKRT_ERR_INVALID, "tonemap: image too large for the mip chain");
     if(total > ctx->mipCapacity)
     {
+      CTX_CHECK(cudaStreamSynchronize(ctx->post));  // an asynchronous tonemap may still read the old pyramid
       cudaFree(ctx->dMips);
       ctx->dMips = nullptr;
       CTX_CHECK(cudaMalloc(&ctx->dMips, std::max<size_t>(total, 1) * sizeof(float4)));
@@ -746,20 +851,33 @@ static int tonemapCommon(vkrt_ctx* ctx, const Tonemapper* tm, float* hostF, uint
     {
       mips.w[l] = std::max(1, mips.w[l - 1] >> 1);
       mips.h[l] = std::max(1, mips.h[l - 1] >> 1);
-      launchMipDown(ctx->stream, mips.level[l - 1], mips.w[l - 1], mips.h[l - 1], dst, mips.w[l], mips.h[l]);
+      launchMipDown(st, mips.level[l - 1], mips.w[l - 1], mips.h[l - 1], dst, mips.w[l], mips.h[l]);
       ctx->stats.kernel_launches++;
       mips.level[l] = dst;
       dst += (size_t)mips.w[l] * mips.h[l];
     }
     mips.count = levels;
   }
-  if(hostF && !ctx->dToneF) CTX_CHECK(cudaMalloc(&ctx->dToneF, n * sizeof(float4)));
-  if(host8 && !ctx->dTone8) CTX_CHECK(cudaMalloc(&ctx->dTone8, n * sizeof(uchar4)));
   {
-    ScopedTimer t(ctx, true, T_TONEMAP);
-    launchTonemap(ctx->stream, ctx->image, ctx->W, ctx->H, *tm, mips, hostF ? ctx->dToneF : nullptr, host8 ? ctx->dTone8 : nullptr);
+    ScopedTimer t(ctx, timed, T_TONEMAP);
+    launchTonemap(st, ctx->image, ctx->W, ctx->H, *tm, mips, dF, d8);
   }
   ctx->stats.kernel_launches++;
+  return VKRT_OK;
+}
+
+static int tonemapCommon(vkrt_ctx* ctx, const Tonemapper* tm, float* hostF, uint8_t* host8)
+{
+  if(!ctx || !tm || !ctx->image) return VKRT_ERR_STATE;
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)ctx->W * ctx->H;
+  if(hostF && !ctx->dToneF) CTX_CHECK(cudaMalloc(&ctx->dToneF, n * sizeof(float4)));
+  if(host8 && !ctx->dTone8) CTX_CHECK(cudaMalloc(&ctx->dTone8, n * sizeof(uchar4)));
+  CTX_CHECK(cudaStreamSynchronize(ctx->post));  // the mip pyramid is shared with vkrt_tonemap_async
+  CTX_CHECK(imageBegin(ctx, ctx->stream));
+  int rc = enqueueTonemap(ctx, ctx->stream, tm, hostF ? ctx->dToneF : nullptr, host8 ? ctx->dTone8 : nullptr, true);
+  if(rc != VKRT_OK) return rc;
+  CTX_CHECK(imageEnd(ctx, ctx->stream));
   if(hostF) CTX_CHECK(cudaMemcpyAsync(hostF, ctx->dToneF, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
   if(host8) CTX_CHECK(cudaMemcpyAsync(host8, ctx->dTone8, n * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->stream));
   CTX_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -768,16 +886,66 @@ static int tonemapCommon(vkrt_ctx* ctx, const Tonemapper* tm, float* hostF, uint
 int vkrt_tonemap(vkrt_ctx* ctx, const Tonemapper* tm, uint8_t* host_rgba8) { return tonemapCommon(ctx, tm, nullptr, host_rgba8); }
 int vkrt_tonemap_float(vkrt_ctx* ctx, const Tonemapper* tm, float* host_rgba32f) { return tonemapCommon(ctx, tm, host_rgba32f, nullptr); }
 
-// ---- render --------------------------------------------------------------------------------------------
-static int ensurePixelList(vkrt_ctx* ctx, int tile, int rank, int count)
+int vkrt_tonemap_async(vkrt_ctx* ctx, const Tonemapper* tm, uint8_t* host_rgba8, int32_t slot)
 {
+  if(!ctx || !tm || !host_rgba8 || slot < 0 || slot > 1) return VKRT_ERR_INVALID;
+  if(!ctx->image) return fail(ctx, VKRT_ERR_STATE, "tonemap_async: no output image");
+  cudaSetDevice(ctx->device);
+  const size_t n = (size_t)ctx->W * ctx->H;
+  if(!ctx->dTone8Async[slot]) CTX_CHECK(cudaMalloc(&ctx->dTone8Async[slot], n * sizeof(uchar4)));
+  // the post stream runs: [wait for the frames enqueued so far] tonemap kernel -> [image free again] -> copy to the host.
+  // Stream order on `post` also keeps the previous use of this staging buffer (its copy) ahead of the kernel that refills it.
+  CTX_CHECK(imageBegin(ctx, ctx->post));
+  int rc = enqueueTonemap(ctx, ctx->post, tm, nullptr, ctx->dTone8Async[slot], false);
+  if(rc != VKRT_OK) return rc;
+  CTX_CHECK(imageEnd(ctx, ctx->post));
+  CTX_CHECK(cudaMemcpyAsync(host_rgba8, ctx->dTone8Async[slot], n * sizeof(uchar4), cudaMemcpyDeviceToHost, ctx->post));
+  CTX_CHECK(cudaEventRecord(ctx->evCopy[slot], ctx->post));
+  ctx->copyPending[slot] = true;
+  return VKRT_OK;
+}
+
+int vkrt_tonemap_wait(vkrt_ctx* ctx, int32_t slot)
+{
+  if(!ctx || slot < 0 || slot > 1) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if(ctx->copyPending[slot])
+  {
+    CTX_CHECK(cudaEventSynchronize(ctx->evCopy[slot]));
+    ctx->copyPending[slot] = false;
+  }
+  return VKRT_OK;
+}
+
+int vkrt_host_alloc(size_t bytes, void** out_ptr)
+{
+  if(!out_ptr) return VKRT_ERR_INVALID;
+  *out_ptr = nullptr;
+  return cudaHostAlloc(out_ptr, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? VKRT_OK : VKRT_ERR_NOMEM;
+}
+int vkrt_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? VKRT_OK : VKRT_ERR_CUDA; }
+
+// ---- tile shards ---------------------------------------------------------------------------------------
+// Tiles are dealt round-robin to the shards; inside a tile pixels are ordered in 8x4 blocks so that a warp of primary rays
+// covers a compact screen footprint.  Lists are cached per (image size, tile, rank, count).
+static int shardList(vkrt_ctx* ctx, int tile, int rank, int count, const vkrt_ctx::ShardList** out)
+{
+  if(tile <= 0) tile = 64;
+  if(count < 1) count = 1;
+  if(count == 1) rank = 0;
+  if(rank < 0 || rank >= count)
+    return fail(ctx, VKRT_ERR_INVALID, "shard_rank out of range");
+  if(!ctx->image)
+    return fail(ctx, VKRT_ERR_STATE, "no output image");
   const int key[5] = {ctx->W, ctx->H, tile, rank, count};
-  if(std::memcmp(key, ctx->shardKey, sizeof(key)) == 0 && ctx->dPixelOfLocal)
-    return VKRT_OK;
-  // Tiles are dealt round-robin to the shards; inside a tile pixels are ordered in 8x4 blocks so that a
-  // warp of primary rays covers a compact screen footprint.
+  for(auto& l : ctx->shardLists)
+    if(std::memcmp(key, l.key, sizeof(key)) == 0)
+    {
+      *out = &l;
+      return VKRT_OK;
+    }
   std::vector<uint32_t> px;
-  px.reserve((size_t)ctx->W * ctx->H / std::max(1, count) + 4096);
+  px.reserve((size_t)ctx->W * ctx->H / (size_t)count + 4096);
   const int tx = (ctx->W + tile - 1) / tile, ty = (ctx->H + tile - 1) / tile;
   for(int t = 0; t < tx * ty; t++)
   {
@@ -791,29 +959,74 @@ static int ensurePixelList(vkrt_ctx* ctx, int tile, int rank, int count)
           for(int x = bx; x < std::min(bx + 8, x1); x++)
             px.push_back((uint32_t)(y * ctx->W + x));
   }
-  if(px.size() > ctx->pixCapacity)
+  if(ctx->shardLists.size() >= 64)
   {
-    cudaFree(ctx->dPixelOfLocal);
+    // bound the cache (a host cycling through many shardings): nothing may still be using the old lists
+    CTX_CHECK(syncAll(ctx));
+    for(auto& l : ctx->shardLists) cudaFree(l.d);
+    ctx->shardLists.clear();
     ctx->dPixelOfLocal = nullptr;
-    CTX_CHECK(cudaMalloc(&ctx->dPixelOfLocal, 4 * std::max<size_t>(px.size(), 1)));
-    ctx->pixCapacity = px.size();
   }
+  vkrt_ctx::ShardList l{};
+  std::memcpy(l.key, key, sizeof(key));
+  l.n = (uint32_t)px.size();
+  CTX_CHECK(cudaMalloc(&l.d, 4 * std::max<size_t>(px.size(), 1)));
   if(!px.empty())
-    CTX_CHECK(cudaMemcpyAsync(ctx->dPixelOfLocal, px.data(), 4 * px.size(), cudaMemcpyHostToDevice, ctx->stream));
-  CTX_CHECK(cudaStreamSynchronize(ctx->stream));
-  std::memcpy(ctx->shardKey, key, sizeof(key));
-  ctx->wf.numLocalPixels = (uint32_t)px.size();
-  ctx->wf.pixelOfLocal   = ctx->dPixelOfLocal;
+    CTX_CHECK(cudaMemcpy(l.d, px.data(), 4 * px.size(), cudaMemcpyHostToDevice));  // synchronous: visible to every stream
+  ctx->shardLists.push_back(l);
+  *out = &ctx->shardLists.back();
   return VKRT_OK;
 }
 
-static int ensureWavefront(vkrt_ctx* ctx, size_t paths)
+int vkrt_output_shard_size(vkrt_ctx* ctx, int32_t tile_size, int32_t shard_rank, int32_t shard_count, uint32_t* out_pixels)
 {
-  if(paths <= ctx->wfCapacity)
+  if(!ctx || !out_pixels) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const vkrt_ctx::ShardList* l = nullptr;
+  int rc = shardList(ctx, tile_size, shard_rank, shard_count, &l);
+  if(rc != VKRT_OK) return rc;
+  *out_pixels = l->n;
+  return VKRT_OK;
+}
+
+int vkrt_output_pack_shard(vkrt_ctx* ctx, int32_t tile_size, int32_t shard_rank, int32_t shard_count, void* device_compact)
+{
+  if(!ctx || !device_compact) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const vkrt_ctx::ShardList* l = nullptr;
+  int rc = shardList(ctx, tile_size, shard_rank, shard_count, &l);
+  if(rc != VKRT_OK) return rc;
+  CTX_CHECK(imageBegin(ctx, ctx->stream));
+  launchShardCopy(ctx->stream, ctx->image, l->d, l->n, (float4*)device_compact, /*toImage=*/false);
+  CTX_CHECK(imageEnd(ctx, ctx->stream));
+  ctx->stats.kernel_launches++;
+  CTX_CHECK(cudaGetLastError());
+  return VKRT_OK;
+}
+
+int vkrt_output_unpack_shard(vkrt_ctx* ctx, int32_t tile_size, int32_t shard_rank, int32_t shard_count, const void* device_compact)
+{
+  if(!ctx || !device_compact) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const vkrt_ctx::ShardList* l = nullptr;
+  int rc = shardList(ctx, tile_size, shard_rank, shard_count, &l);
+  if(rc != VKRT_OK) return rc;
+  CTX_CHECK(imageBegin(ctx, ctx->stream));
+  launchShardCopy(ctx->stream, ctx->image, l->d, l->n, (float4*)device_compact, /*toImage=*/true);
+  CTX_CHECK(imageEnd(ctx, ctx->stream));
+  ctx->stats.kernel_launches++;
+  CTX_CHECK(cudaGetLastError());
+  return VKRT_OK;
+}
+
+// ---- render --------------------------------------------------------------------------------------------
+static int ensureSlot(vkrt_ctx* ctx, WfSlot& sl, size_t paths)
+{
+  if(paths <= sl.capacity)
     return VKRT_OK;
-  const uint32_t keepLocal = ctx->wf.numLocalPixels;
-  freeWavefront(ctx);
-  Wavefront& w = ctx->wf;
+  CTX_CHECK(syncAll(ctx));  // nothing in flight may still use the buffers about to be replaced
+  freeSlot(sl);
+  Wavefront& w = sl.wf;
   const size_t b = paths * sizeof(float4);
   CTX_CHECK(cudaMalloc(&w.rayO, b)); CTX_CHECK(cudaMalloc(&w.rayD, b)); CTX_CHECK(cudaMalloc(&w.hit, b));
   CTX_CHECK(cudaMalloc(&w.thr, b)); CTX_CHECK(cudaMalloc(&w.rad, b)); CTX_CHECK(cudaMalloc(&w.absb, b));
@@ -821,12 +1034,17 @@ static int ensureWavefront(vkrt_ctx* ctx, size_t paths)
   CTX_CHECK(cudaMalloc(&w.shC, b));
   CTX_CHECK(cudaMalloc(&w.queueCur, 4 * paths)); CTX_CHECK(cudaMalloc(&w.queueNext, 4 * paths));
   CTX_CHECK(cudaMalloc(&w.counters, 64));
-  CTX_CHECK(cudaMemsetAsync(w.counters, 0, 64, ctx->stream));
-  ctx->wfCapacity        = paths;
-  w.numLocalPixels       = keepLocal;
-  w.pixelOfLocal         = ctx->dPixelOfLocal;
+  CTX_CHECK(cudaMemsetAsync(w.counters, 0, 64, sl.s));
+  sl.capacity = paths;
   return VKRT_OK;
 }
+
+// first CUDA error of the event plumbing inside the render loop
+struct ErrLatch
+{
+  cudaError_t e = cudaSuccess;
+  void operator()(cudaError_t x) { if(e == cudaSuccess) e = x; }
+};
 
 int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const vkrt_render_opts* opts)
 {
@@ -851,52 +1069,78 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
   const bool heatmap  = state->debugging_mode == VKRT_DBG_HEATMAP;  // per-pixel traversal work instead of a clock (vkrt_shade.cu)
   const bool counting = o.count_traversal != 0 || heatmap;
   const bool timing   = o.profile != 0;  // per-kernel CUDA-event timing
-  // per-kernel timing needs the kernels one after the other; otherwise shadow(b) overlaps closest(b+1) on a second stream
+  // per-kernel timing needs the kernels one after the other; otherwise shadow(b) overlaps closest(b+1) on a second stream and
+  // consecutive batches alternate between the two wavefront slots
   static const bool overlapEnv = []() { const char* e = getenv("VKRT_OVERLAP"); return !e || atoi(e) != 0; }();
+  static const bool dualEnv    = []() { const char* e = getenv("VKRT_DUAL_SLOT"); return !e || atoi(e) != 0; }();
   const bool overlap  = overlapEnv && !timing && !heatmap;
+  const bool dual     = overlap && dualEnv && !o.sort_rays;
   // VKRT_SHADING=precise forces the IEEE-exact shade kernel for callers that cannot pass options (the C++ tools in tests)
   static const bool envPrecise = []() { const char* e = getenv("VKRT_SHADING"); return e && !strcmp(e, "precise"); }();
   if(envPrecise) o.precise_shading = 1;
   if(rank < 0 || rank >= shards)
     return fail(ctx, VKRT_ERR_INVALID, "render: shard_rank out of range");
 
-  int rc = ensurePixelList(ctx, tile, rank, shards);
+  const vkrt_ctx::ShardList* list = nullptr;
+  int rc = shardList(ctx, tile, rank, shards, &list);
   if(rc != VKRT_OK) return rc;
-  const uint32_t nLocal = ctx->wf.numLocalPixels;
+  const uint32_t  nLocal = list->n;
+  const uint32_t* dPix   = list->d;
   if(nLocal == 0)
     return VKRT_OK;
   int fif = o.frames_in_flight;
-  if(fif <= 0)
+  const bool autoFif = fif <= 0;
+  if(autoFif)
   {
-    // automatic: ~64 M paths (11 GB of wavefront state) amortise the latency floor of thin late bounces -- but never more
-    // frames than this call renders (a single interactive frame allocates for one frame), and never more than half of
-    // the memory that is free right now (168 bytes of wavefront state per path, + 12 with the ray sort)
+    // automatic: ~64 M paths in flight (11 GB of wavefront state over the two slots) amortise the latency floor of thin late
+    // bounces -- but never more frames than this call renders (a single interactive frame allocates for one frame), and
+    // never more than half of the memory that is free right now (168 bytes of wavefront state per path, + 12 with the ray sort)
     fif = (int)std::max<size_t>(1, std::min<size_t>(64, (size_t)(64u << 20) / nLocal));
     fif = std::min(fif, num_frames);
+  }
+  // with two slots a batch is half of the frames in flight, so that at least two batches exist to overlap
+  int perBatch = fif;
+  if(dual && std::min(fif, num_frames) >= 2)
+    perBatch = (std::min(fif, num_frames) + 1) / 2;
+  const int slotsNow = (dual && num_frames > perBatch) ? 2 : 1;  // slots this call fills (a one-frame call fills one; the next call the other)
+  if(autoFif)
+  {
+    size_t have = 0;
+    for(int k = 0; k < slotsNow; k++) have += ctx->slots[k].capacity;
     size_t freeB = 0, totalB = 0;
-    if((size_t)nLocal * fif > ctx->wfCapacity && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess)
+    if((size_t)nLocal * perBatch * slotsNow > have && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess)
     {
       const size_t perPath = 10 * sizeof(float4) + 8 + (o.sort_rays ? 12 : 0);
-      const size_t fit     = (freeB / 2 + ctx->wfCapacity * perPath) / (perPath * (size_t)nLocal);
-      fif                  = (int)std::max<size_t>(1, std::min<size_t>((size_t)fif, fit));
+      const size_t fit     = (freeB / 2 + have * perPath) / (perPath * (size_t)nLocal * slotsNow);
+      perBatch             = (int)std::max<size_t>(1, std::min<size_t>((size_t)perBatch, fit));
     }
   }
-  // an explicit frames_in_flight is reserved in full even when this call renders fewer frames, so that a later, longer call
-  // does not reallocate gigabytes in the middle of a render (grow-only)
-  if((uint64_t)nLocal * (uint64_t)fif > 0xffffffffull)
+  // an explicit frames_in_flight is reserved in full (half per slot) even when this call renders fewer frames, so that a
+  // later, longer call does not reallocate gigabytes in the middle of a render (grow-only)
+  const int reserve = std::max(perBatch, autoFif ? 0 : (dual ? (fif + 1) / 2 : fif));
+  if((uint64_t)nLocal * (uint64_t)reserve > 0xffffffffull)
     return fail(ctx, VKRT_ERR_INVALID, "render: pixels x frames_in_flight exceeds 2^32 paths");
-  rc  = ensureWavefront(ctx, (size_t)nLocal * fif);
+  if(slotsNow == 2 || !autoFif)
+    for(int k = 0; k < (dual ? 2 : 1) && rc == VKRT_OK; k++)
+      rc = ensureSlot(ctx, ctx->slots[k], (size_t)nLocal * reserve);
   if(rc == VKRT_OK && o.sort_rays)
-    rc = ensureSortBuffers(ctx, (size_t)nLocal * fif);
-  fif = std::min(fif, num_frames);
+    rc = ensureSortBuffers(ctx, (size_t)nLocal * reserve);
   if(rc != VKRT_OK) return rc;
+  perBatch = std::min(perBatch, num_frames);
 
   TraceStats* dstats = ctx->dStats;
+  ErrLatch    ev;
   for(int done = 0; done < num_frames;)
   {
-    const int batch = std::min(fif, num_frames - done);
-    Wavefront wf    = ctx->wf;
-    wf.numPaths     = nLocal * (uint32_t)batch;
+    const int batch = std::min(perBatch, num_frames - done);
+    WfSlot&   sl    = ctx->slots[dual ? (ctx->nextSlot++ & 1u) : 0u];
+    rc = ensureSlot(ctx, sl, (size_t)nLocal * perBatch);  // no-op once the slot is large enough
+    if(rc != VKRT_OK) return rc;
+    cudaStream_t st = timing ? ctx->stream : sl.s;  // ScopedTimer records on ctx->stream (== slots[0].s; timing is single slot)
+    Wavefront wf      = sl.wf;
+    wf.numPaths       = nLocal * (uint32_t)batch;
+    wf.numLocalPixels = nLocal;
+    wf.pixelOfLocal   = dPix;
     uint32_t* sortAlt = ctx->sortQueueAlt;  // third queue buffer of the optional ray sort (rotates with queueCur)
     FrameParams fp{};
     fp.state         = *state;
@@ -909,7 +1153,7 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
       fp.depth       = 0;
       {
         ScopedTimer t(ctx, timing, T_RAYGEN);
-        launchRaygen(ctx->stream, ctx->view, wf, fp, ctx->numSMs);
+        launchRaygen(st, ctx->view, wf, fp, ctx->numSMs);
       }
       ctx->stats.kernel_launches++;
       for(int depth = 0; depth < state->maxDepth; depth++)
@@ -921,12 +1165,12 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
           // order this bounce's queue by (direction octant, origin Morton code); the live count is read back (one host
           // synchronisation per bounce, only in this mode).  Primary rays are coherent already.
           uint32_t live = 0;
-          CTX_CHECK(cudaMemcpyAsync(&live, wf.counters, 4, cudaMemcpyDeviceToHost, ctx->stream));
-          CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+          CTX_CHECK(cudaMemcpyAsync(&live, wf.counters, 4, cudaMemcpyDeviceToHost, st));
+          CTX_CHECK(cudaStreamSynchronize(st));
           if(live > 64)
           {
             ScopedTimer t(ctx, timing, T_SORT);
-            if(launchSortQueue(ctx->stream, ctx->view, wf.rayO, wf.rayD, wf.queueCur, sortAlt, live, ctx->sortKeysA, ctx->sortKeysB, ctx->sortTemp,
+            if(launchSortQueue(st, ctx->view, wf.rayO, wf.rayD, wf.queueCur, sortAlt, live, ctx->sortKeysA, ctx->sortKeysB, ctx->sortTemp,
                                ctx->sortTempSize))
               std::swap(wf.queueCur, sortAlt);
             ctx->stats.kernel_launches += 1 + 4;  // key kernel + the radix-sort passes of the library
@@ -937,16 +1181,17 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
         L.hit = wf.hit; L.stats = dstats; L.cost = heatmap ? wf.sum : nullptr;
         {
           ScopedTimer t(ctx, timing, T_CLOSEST);
-          launchTraceClosest(ctx->stream, ctx->view, L, counting, ctx->numSMs);
+          ScopedTimer t0(ctx, timing && depth == 0, T_CLOSEST0);
+          launchTraceClosest(st, ctx->view, L, counting, ctx->numSMs);
         }
         if(overlap && depth > 0)
-          cudaStreamWaitEvent(ctx->stream, ctx->evShadow, 0);  // shade(b) adds to the radiance shadow(b-1) resolves into
+          ev(cudaStreamWaitEvent(st, sl.evShadow, 0));  // shade(b) adds to the radiance shadow(b-1) resolves into
         {
           ScopedTimer t(ctx, timing, T_SHADE);
           if(o.precise_shading)
-            launchShadePrecise(ctx->stream, ctx->view, wf, fp, dstats, ctx->numSMs);
+            launchShadePrecise(st, ctx->view, wf, fp, dstats, ctx->numSMs);
           else
-            launchShadeFast(ctx->stream, ctx->view, wf, fp, dstats, ctx->numSMs);
+            launchShadeFast(st, ctx->view, wf, fp, dstats, ctx->numSMs);
         }
         TraceLaunch S{};
         S.rayO = wf.shO; S.rayD = wf.shD; S.queue = nullptr;
@@ -956,47 +1201,64 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
         {
           // the any-hit kernel of this bounce runs beside the closest-hit kernel of the next one: the tail of either
           // persistent kernel is filled by the other's CTAs
-          cudaEventRecord(ctx->evShade, ctx->stream);
-          cudaStreamWaitEvent(ctx->stream2, ctx->evShade, 0);
-          launchTraceShadow(ctx->stream2, ctx->view, S, counting, ctx->numSMs);
-          cudaEventRecord(ctx->evShadow, ctx->stream2);
+          ev(cudaEventRecord(sl.evShade, st));
+          ev(cudaStreamWaitEvent(sl.s2, sl.evShade, 0));
+          launchTraceShadow(sl.s2, ctx->view, S, counting, ctx->numSMs);
+          ev(cudaEventRecord(sl.evShadow, sl.s2));
         }
         else
         {
           ScopedTimer t(ctx, timing, T_SHADOW);
-          launchTraceShadow(ctx->stream, ctx->view, S, counting, ctx->numSMs);
+          ScopedTimer t0(ctx, timing && depth == 0, T_SHADOW0);
+          launchTraceShadow(st, ctx->view, S, counting, ctx->numSMs);
         }
-        launchSwapQueues(ctx->stream, wf, dstats);  // device side: counts; host side: the two id arrays
+        launchSwapQueues(st, wf, dstats, depth == 0);  // device side: counts; host side: the two id arrays
         std::swap(wf.queueCur, wf.queueNext);
         ctx->stats.kernel_launches += 4;
       }
       if(overlap && state->maxDepth > 0)
-        cudaStreamWaitEvent(ctx->stream, ctx->evShadow, 0);
+        ev(cudaStreamWaitEvent(st, sl.evShadow, 0));
       {
         ScopedTimer t(ctx, timing, T_ACCUM);
-        launchFinishSample(ctx->stream, wf, fp, ctx->numSMs);
+        launchFinishSample(st, wf, fp, ctx->numSMs);
       }
       ctx->stats.kernel_launches++;
     }
     {
+      // the running mean is order dependent (pathtrace.comp:126): batches accumulate in frame order, whichever slot they ran on
+      ev(imageBegin(ctx, st));
       ScopedTimer t(ctx, timing, T_ACCUM);
-      launchAccumulate(ctx->stream, wf, fp, ctx->image, ctx->numSMs);
+      launchAccumulate(st, wf, fp, ctx->image, ctx->numSMs);
     }
+    ev(imageEnd(ctx, st));
     ctx->stats.kernel_launches++;
     done += batch;
     ctx->stats.frames_rendered += batch;
     if(ctx->pending.size() > 4096)
       drainTimers(ctx);
   }
+  if(ev.e != cudaSuccess)
+  {
+    ctx->err = std::string("render: stream / event ordering failed: ") + cudaGetErrorString(ev.e);
+    return VKRT_ERR_CUDA;
+  }
   CTX_CHECK(cudaGetLastError());
   return VKRT_OK;
 }
+
 
 int vkrt_sync(vkrt_ctx* ctx)
 {
   if(!ctx) return VKRT_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+  CTX_CHECK(syncAll(ctx));
+  return VKRT_OK;
+}
+
+int vkrt_stream(vkrt_ctx* ctx, void** out_cuda_stream)
+{
+  if(!ctx || !out_cuda_stream) return VKRT_ERR_INVALID;
+  *out_cuda_stream = (void*)ctx->stream;
   return VKRT_OK;
 }
 
@@ -1073,7 +1335,12 @@ int vkrt_mark(vkrt_ctx* ctx, int32_t which)
   if(!ctx || which < 0 || which > 1) return VKRT_ERR_INVALID;
   cudaSetDevice(ctx->device);
   if(!ctx->marks[which]) CTX_CHECK(cudaEventCreate(&ctx->marks[which]));
+  // a mark is a barrier over all streams of the context: everything enqueued before it has finished when it fires, and
+  // nothing enqueued after it starts earlier
+  CTX_CHECK(barrierOn(ctx, ctx->stream));
+  if(ctx->imagePending) CTX_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->evImage, 0));
   CTX_CHECK(cudaEventRecord(ctx->marks[which], ctx->stream));
+  CTX_CHECK(forkFrom(ctx, ctx->stream));
   return VKRT_OK;
 }
 
@@ -1090,7 +1357,7 @@ int vkrt_get_stats(vkrt_ctx* ctx, vkrt_stats* out)
 {
   if(!ctx || !out) return VKRT_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+  CTX_CHECK(syncAll(ctx));
   drainTimers(ctx);
   TraceStats ts{};
   CTX_CHECK(cudaMemcpy(&ts, ctx->dStats, sizeof(ts), cudaMemcpyDeviceToHost));
@@ -1100,6 +1367,7 @@ int vkrt_get_stats(vkrt_ctx* ctx, vkrt_stats* out)
   ctx->stats.tris_tested   = ts.trisTested;
   ctx->stats.shadow_nodes_visited = ts.shadowNodes;
   ctx->stats.shadow_tris_tested   = ts.shadowTris;
+  ctx->stats.shadow_rays_primary  = ts.shadowRaysPrimary;
   ctx->stats.bvh_max_depth        = (uint32_t)ctx->bvh.maxDepth;
   *out = ctx->stats;
   return VKRT_OK;
@@ -1109,7 +1377,7 @@ int vkrt_reset_stats(vkrt_ctx* ctx)
 {
   if(!ctx) return VKRT_ERR_INVALID;
   cudaSetDevice(ctx->device);
-  CTX_CHECK(cudaStreamSynchronize(ctx->stream));
+  CTX_CHECK(syncAll(ctx));
   drainTimers(ctx);
   CTX_CHECK(cudaMemset(ctx->dStats, 0, sizeof(TraceStats)));
   vkrt_stats keep = ctx->stats;

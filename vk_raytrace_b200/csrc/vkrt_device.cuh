@@ -104,7 +104,7 @@ struct Wavefront
 
 struct TraceStats  // device counters
 {
-  unsigned long long closestRays, shadowRays, nodesVisited, trisTested, shadowNodes, shadowTris;
+  unsigned long long closestRays, shadowRays, nodesVisited, trisTested, shadowNodes, shadowTris, shadowRaysPrimary;
 };
 
 }  // namespace vkrt

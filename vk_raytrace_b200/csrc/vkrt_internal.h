@@ -82,7 +82,8 @@ void launchShadePrecise(cudaStream_t s, const SceneView& scene, const Wavefront&
 void launchShadeFast(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs);
 void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, int numSMs);
 void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, int numSMs);
-void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats);
+void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats, bool primary);
+void launchShardCopy(cudaStream_t s, float4* image, const uint32_t* pixels, uint32_t n, float4* compact, bool toImage);
 struct MipView  // RGBA32F mip pyramid of the accumulation image (level 0 = the image itself)
 {
   const float4* level[16];

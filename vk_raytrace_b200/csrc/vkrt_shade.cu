@@ -564,10 +564,14 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(cons
 
 #ifndef VKRT_FAST_MATH
 // After the shadow pass of a bounce: next -> cur, reset cursors, count shadow rays.
-__global__ void swapQueuesKernel(Wavefront wf, TraceStats* stats)
+__global__ void swapQueuesKernel(Wavefront wf, TraceStats* stats, bool primary)
 {
   if(stats)
+  {
     atomicAdd(&stats->shadowRays, (unsigned long long)wf.counters[wf.shadowSlot ? 5 : 2]);
+    if(primary)
+      atomicAdd(&stats->shadowRaysPrimary, (unsigned long long)wf.counters[wf.shadowSlot ? 5 : 2]);
+  }
   wf.counters[0] = wf.counters[1];
   wf.counters[1] = 0;
   wf.counters[3] = 0;
@@ -800,7 +804,24 @@ void VKRT_LAUNCH_SHADE(cudaStream_t s, const SceneView& scene, const Wavefront& 
     launchShadeT<1>(s, scene, wf, fp, stats, numSMs);
 }
 #ifndef VKRT_FAST_MATH
-void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats) { swapQueuesKernel<<<1, 1, 0, s>>>(wf, stats); }
+void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats, bool primary) { swapQueuesKernel<<<1, 1, 0, s>>>(wf, stats, primary); }
+// tile shards: image[pixels[i]] <-> compact[i] (multi-GPU exchange of owned pixels instead of a full-image reduce)
+__global__ void __launch_bounds__(256) shardCopyKernel(float4* __restrict__ image, const uint32_t* __restrict__ pixels, uint32_t n,
+                                                       float4* __restrict__ compact, bool toImage)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i >= n)
+    return;
+  if(toImage)
+    image[pixels[i]] = compact[i];
+  else
+    compact[i] = image[pixels[i]];
+}
+void launchShardCopy(cudaStream_t s, float4* image, const uint32_t* pixels, uint32_t n, float4* compact, bool toImage)
+{
+  if(n)
+    shardCopyKernel<<<(n + 255) / 256, 256, 0, s>>>(image, pixels, n, compact, toImage);
+}
 void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, int)
 {
   finishSampleKernel<<<(wf.numPaths + 255) / 256, 256, 0, s>>>(wf, fp);

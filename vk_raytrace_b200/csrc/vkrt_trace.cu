@@ -46,6 +46,9 @@ namespace vkrt {
 #ifndef VKRT_TRACE_BLOCK
 #define VKRT_TRACE_BLOCK 128
 #endif
+#ifndef VKRT_BRANCHFREE
+#define VKRT_BRANCHFREE 1  // 0: the branchy push / pop / park of round 1 (A/B builds)
+#endif
 constexpr int      kTraceBlock       = VKRT_TRACE_BLOCK;
 constexpr int      kStackShared      = VKRT_STACK_SHARED;  // entries per thread in shared memory
 constexpr int      kStackLocal       = 128 - VKRT_STACK_SHARED;  // overflow entries in local memory
@@ -141,6 +144,7 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
   const uint4* __restrict__  qnodes = sc.qnodes;
   const float4* __restrict__ cnodes = sc.cnodes;
   constexpr bool QN = (FMT == FMT_Q32);
+  constexpr bool BRANCHFREE = (kStackShared >= 4) && (VKRT_BRANCHFREE != 0);
   const float4* __restrict__ tris   = sc.tris;
 
   // per-lane ray + traversal state (lives across refills)
@@ -238,6 +242,14 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
       while(node != kDone || leaf != 0)
       {
         // ---- inner nodes, until every lane of the warp has parked a leaf ---------------------
+        // s1 / s2: the two topmost stack entries as of the start of an iteration (branch-free step; junk below the bottom,
+        // guarded by sp where they are used).  The leaf phase and the refill change the stack, so they are re-read here.
+        uint32_t s1 = 0, s2 = 0;
+        if(BRANCHFREE)
+        {
+          s1 = sstack[max(min(sp, kStackShared) - 1, 0) * kTraceBlock];
+          s2 = sstack[max(min(sp, kStackShared) - 2, 0) * kTraceBlock];
+        }
         while(node < kDone)  // inner index (leaf codes have bit 31 set, kDone is larger than any index)
         {
           float    tn0, tf0, tn1, tf1;
@@ -301,6 +313,36 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
           const float x0 = tf0 * 1.0002f, x1 = tf1 * 1.0002f;
           const bool  h0 = (FMT == FMT_CE) ? (tn0 <= x0 && x0 >= 0.0f) : (tn0 <= x0);
           const bool  h1 = (FMT == FMT_CE) ? (tn1 <= x1 && x1 >= 0.0f) : (tn1 <= x1);
+          if(BRANCHFREE && sp < kStackShared)
+          {
+            // Branch-free step (round 2; ncu of round 1: the push / pop / park branches below ran with 2-4 lanes each and cost as
+            // many issue slots as the 21-lane box test).  The two topmost stack entries were fetched at the top of the iteration
+            // (the address depends on sp only, so the loads are off the node-fetch dependency chain); push, pop and leaf
+            // parking become selects over {far child, top, second}:
+            //   push  far child when both boxes are hit (the store always happens: slot sp is free)
+            //   pop   when neither is hit
+            //   park  when the next node is a leaf and none is parked yet: take the following stack entry
+            const bool     both = h0 && h1, none = !(h0 || h1);
+            const bool     sw   = both && (tn1 < tn0);
+            const uint32_t nearC = (h0 && !sw) ? c0 : c1;
+            const uint32_t farC  = sw ? c0 : c1;
+            sstack[sp * kTraceBlock] = farC;
+            const uint32_t t1 = both ? farC : s1, t2 = both ? s1 : s2;
+            int            spn = sp + (both ? 1 : 0);
+            const bool     popped = none && spn > 0;
+            const uint32_t nd = none ? (popped ? t1 : kDone) : nearC;
+            const uint32_t u1 = popped ? t2 : t1;
+            spn -= popped ? 1 : 0;
+            const bool park = (nd & kLeafBit) && leaf == 0;
+            leaf            = park ? nd : leaf;
+            node            = park ? (spn > 0 ? u1 : kDone) : nd;
+            sp              = spn - ((park && spn > 0) ? 1 : 0);
+            // the next iteration's view of the stack top, fetched now so that the shared-memory latency overlaps the node fetch
+            s1 = sstack[max(min(sp, kStackShared) - 1, 0) * kTraceBlock];
+            s2 = sstack[max(min(sp, kStackShared) - 2, 0) * kTraceBlock];
+          }
+          else
+          {
           if(h0 && h1)
           {
             if(tn1 < tn0)
@@ -321,6 +363,12 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
           {
             leaf = node;
             node = pop();
+          }
+          if(BRANCHFREE)
+          {
+            s1 = sstack[max(min(sp, kStackShared) - 1, 0) * kTraceBlock];
+            s2 = sstack[max(min(sp, kStackShared) - 2, 0) * kTraceBlock];
+          }
           }
           if(VARIANT == 0)
           {

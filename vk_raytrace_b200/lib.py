@@ -26,6 +26,8 @@ EXPORTS = [
     "vkrt_output_device_ptr", "vkrt_output_clear", "vkrt_output_read", "vkrt_tonemap", "vkrt_tonemap_float", "vkrt_render",
     "vkrt_sync", "vkrt_pack_vertices", "vkrt_make_camera", "vkrt_light_from_matrix", "vkrt_trace_rays", "vkrt_triangle_ids",
     "vkrt_get_stats", "vkrt_reset_stats", "vkrt_mark", "vkrt_elapsed_ms",
+    "vkrt_tonemap_async", "vkrt_tonemap_wait", "vkrt_host_alloc", "vkrt_host_free",
+    "vkrt_stream", "vkrt_output_shard_size", "vkrt_output_pack_shard", "vkrt_output_unpack_shard",
 ]
 
 
@@ -72,5 +74,13 @@ def load_library():
     lib.vkrt_reset_stats.argtypes = [vp]
     lib.vkrt_mark.argtypes = [vp, i32]
     lib.vkrt_elapsed_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.vkrt_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.vkrt_tonemap_async.argtypes = [vp, C.POINTER(S.Tonemapper), vp, i32]
+    lib.vkrt_tonemap_wait.argtypes = [vp, i32]
+    lib.vkrt_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.vkrt_host_free.argtypes = [vp]
+    lib.vkrt_output_shard_size.argtypes = [vp, i32, i32, i32, C.POINTER(u32)]
+    lib.vkrt_output_pack_shard.argtypes = [vp, i32, i32, i32, vp]
+    lib.vkrt_output_unpack_shard.argtypes = [vp, i32, i32, i32, vp]
     _LIB = lib
     return lib

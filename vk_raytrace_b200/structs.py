@@ -44,7 +44,8 @@ class Stats(C.Structure):
                 ("ms_trace_closest", C.c_double), ("ms_trace_shadow", C.c_double), ("ms_shade", C.c_double), ("ms_sort", C.c_double),
                 ("ms_accumulate", C.c_double), ("ms_tonemap", C.c_double), ("ms_build", C.c_double), ("num_triangles", u32),
                 ("num_bvh_nodes", u32), ("num_instances", u32), ("has_non_opaque", u32), ("shadow_nodes_visited", C.c_uint64),
-                ("shadow_tris_tested", C.c_uint64), ("bvh_max_depth", u32), ("node_bytes", u32), ("bvh_width", u32), ("_pad", u32), ("reserved", C.c_double * 4)]
+                ("shadow_tris_tested", C.c_uint64), ("bvh_max_depth", u32), ("node_bytes", u32), ("bvh_width", u32), ("_pad", u32), ("ms_trace_closest_primary", C.c_double),
+                ("ms_trace_shadow_primary", C.c_double), ("shadow_rays_primary", C.c_uint64), ("reserved", C.c_double * 1)]
 
 
 # numpy dtypes for the bulk arrays (packed, identical to the C structs)
