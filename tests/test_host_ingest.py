@@ -160,3 +160,160 @@ def test_gltf_import_matches_exported_scene(selftest, tmp_path):
     open(glb, "wb").write(struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(js) + 8 + len(binb)) + struct.pack("<II", len(js), 0x4E4F534A) + js + struct.pack("<II", len(binb), 0x004E4942) + binb)
     out2 = subprocess.run([selftest, "gltf", glb], capture_output=True, text=True)
     assert out2.returncode == 0 and out2.stdout.splitlines()[1] == lines[1]
+
+
+def decode_image(selftest, path, tmp_path):
+    raw = str(tmp_path / "out.raw")
+    out = subprocess.run([selftest, "jpg", path, raw], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    w, h = map(int, out.stdout.split())
+    return np.fromfile(raw, dtype=np.uint8).reshape(h, w, 4)
+
+
+def _photo(h, w, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([128 + 100 * np.sin(xx / 9.0) * np.cos(yy / 7.0), 128 + 90 * np.sin((xx + yy) / 11.0), 128 + 80 * np.cos(xx / 5.0 + yy / 13.0)], -1)
+    return np.clip(img + rng.normal(0, 12, (h, w, 3)), 0, 255).astype(np.uint8)
+
+
+def test_jpeg_decoder_matches_pillow_exactly(selftest, tmp_path):
+    """Baseline / progressive, 4:4:4 / 4:2:2 / 4:2:0 / grey, optimised tables, restart intervals, odd sizes: the decoder implements the IJG
+    reference arithmetic (islow IDCT, triangle upsampling, 16-bit YCbCr conversion), so it must equal Pillow (libjpeg-turbo) bit for bit."""
+    from PIL import Image
+    n = 0
+    for (h, w) in ((64, 64), (37, 53), (100, 131), (8, 8), (1, 1), (3, 2), (17, 5), (250, 16)):
+        img = _photo(h, w, h * 131 + w)
+        for name, kw in (("444", dict(subsampling=0)), ("422", dict(subsampling=1)), ("420", dict(subsampling=2)),
+                         ("prog420", dict(subsampling=2, progressive=True)), ("prog444", dict(subsampling=0, progressive=True)), ("grey", dict()),
+                         ("q30", dict(quality=30, subsampling=2)), ("q100", dict(quality=100, subsampling=0)), ("opt", dict(optimize=True, subsampling=2)),
+                         ("rst", dict(subsampling=2, restart_marker_blocks=3)), ("rstprog", dict(subsampling=1, progressive=True, restart_marker_rows=1))):
+            p = str(tmp_path / f"{name}.jpg")
+            kw = dict(kw)
+            Image.fromarray(img if name != "grey" else img[..., 0].copy()).save(p, quality=kw.pop("quality", 90), **kw)
+            got = decode_image(selftest, p, tmp_path)
+            want = np.asarray(Image.open(p).convert("RGBA"))
+            assert np.array_equal(got, want), (h, w, name, int(np.abs(got.astype(int) - want.astype(int)).max()))
+            n += 1
+    assert n > 80
+    # garbage and truncation are errors, not crashes
+    blob = open(str(tmp_path / "420.jpg"), "rb").read()
+    for bad in (blob[:100], blob[:len(blob) // 2], b"\xff\xd8\xff" + bytes(200), blob[:20] + bytes(64) + blob[84:]):
+        p = str(tmp_path / "bad.jpg")
+        open(p, "wb").write(bad)
+        out = subprocess.run([selftest, "jpg", p, str(tmp_path / "o.raw")], capture_output=True, text=True)
+        assert out.returncode in (0, 2), out.returncode      # decoded partially or rejected; never a signal
+
+
+def test_gltf_jpeg_textures_and_sparse_accessors(selftest, tmp_path):
+    """A hand-written glTF with what the real Khronos assets use and round 1 lacked: JPEG images (external file and base64 data URI)
+    and sparse accessors (with and without a base bufferView, glTF 2.0 section 3.6.2.3)."""
+    import base64
+    import io
+    import json
+    from PIL import Image
+    tex_a, tex_b = _photo(32, 48, 1), _photo(16, 16, 2)
+    Image.fromarray(tex_a).save(str(tmp_path / "a.jpg"), quality=85, subsampling=2)
+    bio = io.BytesIO()
+    Image.fromarray(tex_b).save(bio, "JPEG", quality=92, subsampling=0, progressive=True)
+    want_tex = 0.0
+    for src in (str(tmp_path / "a.jpg"), bio):
+        if not isinstance(src, str):
+            src.seek(0)
+        im = np.asarray(Image.open(src).convert("RGBA")).astype(np.float64)
+        want_tex += im.sum() + 1000003.0 * im.shape[1] + 7919.0 * im.shape[0]
+    base = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], np.float32)
+    idx = np.array([0, 1, 2, 2, 1, 3], np.uint16)
+    sp_idx = np.array([1, 3], np.uint8)                         # replace vertices 1 and 3
+    sp_val = np.array([[2, 0, 0.5], [2, 2, -1]], np.float32)
+    sp2_idx = np.array([0, 2], np.uint16)                       # second mesh: zero base, two vertices set
+    sp2_val = np.array([[0, 0, 1], [0, 3, 1]], np.float32)
+    blob = b""
+    views = []
+
+    def add(data):
+        nonlocal blob
+        blob += b"\0" * (-len(blob) % 4)
+        views.append({"buffer": 0, "byteOffset": len(blob), "byteLength": len(data)})
+        blob += data
+        return len(views) - 1
+    v_base, v_idx, v_si, v_sv, v_s2i, v_s2v = (add(a.tobytes()) for a in (base, idx, sp_idx, sp_val, sp2_idx, sp2_val))
+    open(str(tmp_path / "m.bin"), "wb").write(blob)
+    doc = {
+        "asset": {"version": "2.0"}, "scene": 0, "scenes": [{"nodes": [0, 1]}],
+        "nodes": [{"mesh": 0}, {"mesh": 1, "translation": [0, 0, 2]}],
+        "buffers": [{"uri": "m.bin", "byteLength": len(blob)}], "bufferViews": views,
+        "accessors": [
+            {"bufferView": v_base, "componentType": 5126, "count": 4, "type": "VEC3",
+             "sparse": {"count": 2, "indices": {"bufferView": v_si, "componentType": 5121}, "values": {"bufferView": v_sv}}},
+            {"bufferView": v_idx, "componentType": 5123, "count": 6, "type": "SCALAR"},
+            {"componentType": 5126, "count": 3, "type": "VEC3",
+             "sparse": {"count": 2, "indices": {"bufferView": v_s2i, "componentType": 5123}, "values": {"bufferView": v_s2v}}}],
+        "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1, "material": 0}]},
+                   {"primitives": [{"attributes": {"POSITION": 2}, "material": 0}]}],
+        "materials": [{"pbrMetallicRoughness": {"baseColorTexture": {"index": 0}, "metallicRoughnessTexture": {"index": 1}}}],
+        "textures": [{"source": 0}, {"source": 1}],
+        "images": [{"uri": "a.jpg"}, {"uri": "data:image/jpeg;base64," + base64.b64encode(bio.getvalue()).decode()}],
+    }
+    p = str(tmp_path / "m.gltf")
+    json.dump(doc, open(p, "w"))
+    out = subprocess.run([selftest, "gltf", p], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    sums = dict(zip(lines[1].split()[0::2], map(float, lines[1].split()[1::2])))
+    pos0 = base.copy()
+    pos0[sp_idx] = sp_val
+    pos1 = np.zeros((3, 3), np.float32)
+    pos1[sp2_idx] = sp2_val
+    assert abs(sums["sumPos"] - float(pos0.sum() + pos1.sum())) < 1e-5
+    assert sums["sumTex"] == want_tex
+    assert "primMeshes 2 nodes 2 triangles 3" in lines[0] and "textures 2" in lines[0]
+    # malformed files fail with a message instead of reading out of bounds or looping
+    bad = json.loads(json.dumps(doc))
+    bad["accessors"].append({"bufferView": v_base, "componentType": 5126, "count": 3, "type": "VEC3"})
+    bad["meshes"][0]["primitives"][0]["attributes"]["NORMAL"] = 3          # 3 normals for 4 positions
+    json.dump(bad, open(str(tmp_path / "bad1.gltf"), "w"))
+    out = subprocess.run([selftest, "gltf", str(tmp_path / "bad1.gltf")], capture_output=True, text=True)
+    assert out.returncode == 2 and "different count" in out.stderr
+    bad = json.loads(json.dumps(doc))
+    bad["nodes"] = [{"children": [1]}, {"children": [0], "mesh": 0}]       # cycle
+    json.dump(bad, open(str(tmp_path / "bad2.gltf"), "w"))
+    out = subprocess.run([selftest, "gltf", str(tmp_path / "bad2.gltf")], capture_output=True, text=True, timeout=20)
+    assert out.returncode == 2 and "cyclic" in out.stderr
+    bad = json.loads(json.dumps(doc))
+    bad["accessors"][0]["sparse"]["indices"]["componentType"] = 5126       # float indices are not allowed
+    json.dump(bad, open(str(tmp_path / "bad3.gltf"), "w"))
+    assert subprocess.run([selftest, "gltf", str(tmp_path / "bad3.gltf")], capture_output=True, text=True).returncode == 2
+
+
+def test_png_header_validation(selftest, tmp_path):
+    """crafted IHDR fields (bad length, illegal bit depth, absurd size, data that does not match the header) are errors."""
+    import zlib
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    def png(ihdr, raw, ihdr_extra=b""):
+        return b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr + ihdr_extra) + chunk(b"IDAT", zlib.compress(raw)) + chunk(b"IEND", b"")
+    good_raw = b"".join(b"\x00" + bytes([10, 20, 30] * 4) for _ in range(3))
+    cases = {
+        "ok": (png(struct.pack(">IIBBBBB", 4, 3, 8, 2, 0, 0, 0), good_raw), 0),
+        "depth0": (png(struct.pack(">IIBBBBB", 4, 3, 0, 0, 0, 0, 0), good_raw), 2),
+        "depth3": (png(struct.pack(">IIBBBBB", 4, 3, 3, 3, 0, 0, 0), good_raw), 2),
+        "depth4_rgb": (png(struct.pack(">IIBBBBB", 4, 3, 4, 2, 0, 0, 0), good_raw), 2),
+        "huge": (png(struct.pack(">IIBBBBB", 0xFFFFFFFF, 0x40000001, 1, 0, 0, 0, 0), good_raw), 2),
+        "long_ihdr": (png(struct.pack(">IIBBBBB", 4, 3, 8, 2, 0, 0, 0), good_raw, b"\0\0"), 2),
+        "short_data": (png(struct.pack(">IIBBBBB", 4, 30, 8, 2, 0, 0, 0), good_raw), 2),
+        "long_data": (png(struct.pack(">IIBBBBB", 4, 2, 8, 2, 0, 0, 0), good_raw), 2),
+        "filter_method": (png(struct.pack(">IIBBBBB", 4, 3, 8, 2, 0, 1, 0), good_raw), 2),
+    }
+    for name, (blob, want) in cases.items():
+        p = str(tmp_path / f"{name}.png")
+        open(p, "wb").write(blob)
+        out = subprocess.run([selftest, "png", p, str(tmp_path / "o.raw")], capture_output=True, text=True)
+        assert out.returncode == want, (name, out.returncode, out.stderr)
+    # Radiance header with negative / absurd dimensions
+    for dims in ("-Y -5 +X 64", "-Y 5 +X 99999999"):
+        p = str(tmp_path / "bad.hdr")
+        open(p, "wb").write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n" + dims.encode() + b"\n" + bytes(64))
+        assert subprocess.run([selftest, "hdr", p, str(tmp_path / "o.raw")], capture_output=True, text=True).returncode == 2

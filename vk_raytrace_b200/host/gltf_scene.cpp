@@ -391,7 +391,7 @@ bool loadGltf(const std::string& path, GltfSceneData& out, std::string& err)
   if(out.materials.empty())
     out.materials.push_back(defaultMaterial());
 
-  // textures: tinygltf decodes every image to RGBA8 (src/scene.cpp:527-541); undecodable -> 1x1 white (scene.cpp:496-502)
+  // textures: tinygltf decodes every image (PNG, JPEG) to RGBA8 (src/scene.cpp:527-541); undecodable -> 1x1 white (scene.cpp:496-502)
   const mj::Value& jtex = d.root["textures"];
   const mj::Value& jimg = d.root["images"];
   const mj::Value& jsmp = d.root["samplers"];
@@ -417,7 +417,7 @@ bool loadGltf(const std::string& path, GltfSceneData& out, std::string& err)
       }
     }
     std::string ierr;
-    if(bytes.empty() || !decodePng(bytes.data(), bytes.size(), images[i], ierr))
+    if(bytes.empty() || !decodeImage(bytes.data(), bytes.size(), images[i], ierr))
     {
       images[i].w = images[i].h = 1;
       images[i].rgba = {255, 255, 255, 255};

@@ -1,8 +1,8 @@
 // image_io.cpp -- the image decoders the reference gets from stb_image through tinygltf / stbi_loadf
 // (src/scene.cpp:527-541 textures -> RGBA8, src/hdr_sampling.cpp:64 environment -> RGBA32F), restated without the
 // dependency: PNG (8/16-bit, all colour types, non-interlaced and Adam7) with an inflate implementation, Radiance .hdr
-// (RGBE, flat and new-style RLE) and PFM (exact float, used by the tests).  JPEG is not decoded: such textures fall
-// back to the 1x1 white image exactly like the reference's addDefaultImage (src/scene.cpp:496-502).
+// (RGBE, flat and new-style RLE) and PFM (exact float, used by the tests); JPEG lives in jpeg_decode.cpp.  Anything else
+// (and any file that fails to decode) falls back to the 1x1 white image like the reference's addDefaultImage (src/scene.cpp:496-502).
 #include "image_io.hpp"
 #include <cmath>
 #include <cstdio>
@@ -297,6 +297,13 @@ bool decodePng(const uint8_t* data, size_t size, ImageRGBA8& out, std::string& e
   }
   if(!ok) { err = "PNG data too short"; return false; }
   return true;
+}
+
+bool decodeImage(const uint8_t* data, size_t size, ImageRGBA8& out, std::string& err)
+{
+  if(size >= 3 && data[0] == 0xFF && data[1] == 0xD8 && data[2] == 0xFF)
+    return decodeJpeg(data, size, out, err);
+  return decodePng(data, size, out, err);
 }
 
 // ---- Radiance RGBE (.hdr) and PFM -> RGBA32F, alpha = 1 (stbi_loadf(..., STBI_rgb_alpha)) ---------------------------------

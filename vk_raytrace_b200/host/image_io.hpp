@@ -19,6 +19,10 @@ struct ImageRGBA32F
 
 bool readFile(const std::string& path, std::vector<uint8_t>& out);
 bool decodePng(const uint8_t* data, size_t size, ImageRGBA8& out, std::string& err);
+// baseline / extended / progressive Huffman JPEG, 1 or 3 components (jpeg_decode.cpp)
+bool decodeJpeg(const uint8_t* data, size_t size, ImageRGBA8& out, std::string& err);
+// PNG or JPEG by signature
+bool decodeImage(const uint8_t* data, size_t size, ImageRGBA8& out, std::string& err);
 bool loadHdrOrPfm(const std::string& path, ImageRGBA32F& out, std::string& err);
 
 }  // namespace vkrt_host
