@@ -216,7 +216,7 @@ def main():
     ap.add_argument("--build-mode", type=int, default=-1,
                     help="-1 auto (default): the best-tracing builder that is still quick at load time, as the reference asks its driver for "
                          "(PREFER_FAST_TRACE, src/accelstruct.cpp:125): host binned SAH up to 2 M triangles, GPU LBVH + leaf collapse above; "
-                         "0 GPU LBVH, 1 GPU LBVH + SAH leaf collapse, 2 host binned SAH, 3 GPU PLOC + SAH leaf collapse")
+                         "0 GPU LBVH, 1 GPU LBVH + SAH leaf collapse, 2 host binned SAH, 3 GPU PLOC + SAH leaf collapse, 4 GPU binned SAH")
     ap.add_argument("--frames-in-flight", type=int, default=0)
     ap.add_argument("--sort-rays", action="store_true", help="vkrt_render_opts.sort_rays: order each bounce's queue by octant + origin Morton key")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -557,7 +557,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": args.workload, "scene": scene.name, "triangles": int(s.num_triangles), "bvh_nodes": int(s.num_bvh_nodes),
-                           "bvh_build": {"mode": {0: "lbvh", 1: "lbvh+leaf-collapse", 2: "host-sah", 3: "ploc+leaf-collapse"}[args.build_mode],
+                           "bvh_build": {"mode": {0: "lbvh", 1: "lbvh+leaf-collapse", 2: "host-sah", 3: "ploc+leaf-collapse", 4: "gpu-binned-sah"}[args.build_mode],
                                          "ms": float(s.ms_build), "bvh_width": int(s.bvh_width), "max_depth": int(s.bvh_max_depth),
                                          "what": "vkrt_scene_commit: instance flattening + BVH build, outside the timed region (SURVEY 8d)"},
                            "resolution": [W, H], "max_depth": cfg["depth"], "spp_per_step": 1, "pbr_mode": args.pbr_mode,

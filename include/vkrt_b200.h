@@ -45,6 +45,8 @@ typedef struct vkrt_ctx vkrt_ctx;
 #define VKRT_BUILD_LBVH_COLLAPSED 1 /* LBVH + bottom-up SAH leaf collapse */
 #define VKRT_BUILD_SAH_HOST 2       /* GPU flatten + host binned-SAH BVH2 (slow build, fast trace) */
 #define VKRT_BUILD_PLOC 3           /* GPU: Morton sort + parallel locally-ordered clustering + SAH leaf collapse (SAH-like quality) */
+#define VKRT_BUILD_SAH_GPU 4        /* GPU: breadth-first binned SAH (32 bins, triangle-parallel) as path-code keys + radix tree + SAH leaf collapse:
+                                       the PREFER_FAST_TRACE builder (src/accelstruct.cpp:125), a few ms for 260 k triangles */
 #define VKRT_BUILD_MODE_MASK 0xff
 /* OR-ed into build_mode: which tree the traversal kernels walk for this scene, overriding the size rule
  * (binary while the BVH fits the L2, 4-wide above 1.5 M triangles) and the VKRT_BVH_WIDTH environment switch. */
@@ -66,7 +68,10 @@ typedef struct vkrt_render_opts
   int32_t precise_shading;  /* 0 (default): the shade kernel uses approximate division / sqrt and SFU sin/cos/exp/log/pow, as a GLSL
                                compiler does; 1: IEEE-exact arithmetic throughout (what the oracle comparisons at 1e-4 use).
                                Ray generation, traversal and intersection are exact in both. */
-  int32_t reserved[7];
+  int32_t tail_from;        /* bounce from which one fused kernel (trace + shade + shadow per path) finishes the few paths still alive:
+                               0 = automatic (bounce 3 for small wavefronts: interactive frames, thin shards), -1 = never, n > 0 = from
+                               bounce n.  Same image in every setting. */
+  int32_t reserved[6];
 } vkrt_render_opts;
 
 typedef struct vkrt_stats
@@ -100,7 +105,7 @@ typedef struct vkrt_stats
   double   ms_trace_closest_primary;
   double   ms_trace_shadow_primary;
   uint64_t shadow_rays_primary;
-  double   reserved[1];
+  double   ms_tail;         /* fused tail kernel: the late bounces of small wavefronts in one launch (trace + shade + shadow) */
 } vkrt_stats;
 
 /* ---- context ---------------------------------------------------------- */

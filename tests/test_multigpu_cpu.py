@@ -26,10 +26,25 @@ def _worker(rank, world, port, out_path):
     o.render_tiles(st, 3, tile=16, shard_rank=rank, shard_count=world)
     img = torch.from_numpy(o.output_read())
     rays = torch.tensor([sum(o.counters()[k] for k in ("closest_rays", "shadow_rays"))], dtype=torch.int64)
+    # exchange 2 (round 2, what bench.py does on NCCL): every rank sends only the pixels it owns, in shard order, padded to the
+    # largest shard; the root scatters them.  1 / world of the bytes of the zero-padded reduce below, same image.
+    from vk_raytrace_b200.context import shard_pixel_list
+    lists = [shard_pixel_list(W, H, 16, r, world) for r in range(world)]
+    cap = max(len(l) for l in lists)
+    mine = torch.zeros((cap, 4), dtype=torch.float32)
+    mine[: len(lists[rank])] = img.reshape(-1, 4)[torch.from_numpy(lists[rank].astype(np.int64))]
+    gathered = [torch.zeros((cap, 4), dtype=torch.float32) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, gathered, dst=0)
+    rebuilt = None
+    if rank == 0:
+        rebuilt = img.clone().reshape(-1, 4)
+        for r in range(1, world):
+            rebuilt[torch.from_numpy(lists[r].astype(np.int64))] = gathered[r][: len(lists[r])]
+        rebuilt = rebuilt.reshape(H, W, 4)
     dist.reduce(img, 0)
     dist.all_reduce(rays)
     if rank == 0:
-        np.savez(out_path, img=img.numpy(), rays=rays.numpy())
+        np.savez(out_path, img=img.numpy(), rays=rays.numpy(), rebuilt=rebuilt.numpy(), shard_sizes=np.array([len(l) for l in lists]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -46,5 +61,7 @@ def test_two_rank_tile_shards_reduce_to_the_whole_image(tmp_path, ob):
     st = S.default_rtx_state(W, H, maxDepth=3)
     o.render(st, 3)
     assert np.array_equal(got["img"], o.output_read())
+    assert np.array_equal(got["rebuilt"], o.output_read())          # gather of owned pixels == reduce of zero-padded images
+    assert int(got["shard_sizes"].sum()) == W * H
     c = o.counters()
     assert int(got["rays"][0]) == c["closest_rays"] + c["shadow_rays"]

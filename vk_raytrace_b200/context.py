@@ -46,6 +46,26 @@ class SceneDesc:
         return sum(len(self.meshes[m].indices) // 3 for _, m in self.nodes)
 
 
+def shard_pixel_list(width, height, tile, rank, count):
+    """Pixels (y * width + x) of the tile shard (tile, rank, count) in the order the library stores them -- tiles dealt round-robin
+    (t % count == rank), 8x4 pixel blocks inside a tile: the host-side mirror of vkrt_output_pack_shard / _unpack_shard, used by the
+    CPU multi-process test and by hosts that post-process gathered shards themselves."""
+    tile = tile if tile > 0 else 64
+    tx, ty = (width + tile - 1) // tile, (height + tile - 1) // tile
+    out = []
+    for t in range(tx * ty):
+        if count > 1 and t % count != rank:
+            continue
+        x0, y0 = (t % tx) * tile, (t // tx) * tile
+        x1, y1 = min(x0 + tile, width), min(y0 + tile, height)
+        for by in range(y0, y1, 4):
+            for bx in range(x0, x1, 8):
+                ys = np.arange(by, min(by + 4, y1))[:, None]
+                xs = np.arange(bx, min(bx + 8, x1))[None, :]
+                out.append((ys * width + xs).reshape(-1))
+    return np.concatenate(out).astype(np.uint32) if out else np.zeros(0, np.uint32)
+
+
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 

@@ -38,7 +38,7 @@ struct HostTexture
   int32_t              linear, wrapS, wrapT;
 };
 
-enum TimerSlot { T_RAYGEN = 0, T_CLOSEST, T_SHADOW, T_SHADE, T_SORT, T_ACCUM, T_TONEMAP, T_CLOSEST0, T_SHADOW0, T_COUNT };
+enum TimerSlot { T_RAYGEN = 0, T_CLOSEST, T_SHADOW, T_SHADE, T_SORT, T_ACCUM, T_TONEMAP, T_CLOSEST0, T_SHADOW0, T_TAIL, T_COUNT };
 
 // One wavefront in flight: its path state, its two streams (closest-hit / shade, and the any-hit kernels that overlap the next
 // bounce) and the events that order them.  A context owns two: consecutive batches -- the halves of a multi-frame render, or
@@ -284,6 +284,7 @@ static void drainTimers(vkrt_ctx* c)
   c->stats.ms_tonemap += acc[T_TONEMAP];
   c->stats.ms_trace_closest_primary += acc[T_CLOSEST0];
   c->stats.ms_trace_shadow_primary += acc[T_SHADOW0];
+  c->stats.ms_tail += acc[T_TAIL];
 }
 
 struct ScopedTimer
@@ -473,7 +474,7 @@ int vkrt_scene_commit(vkrt_ctx* ctx, int32_t build_mode)
   if((build_mode & ~(VKRT_BUILD_MODE_MASK | VKRT_BUILD_FORCE_BVH2 | VKRT_BUILD_FORCE_BVH4)) || widthFlags == (VKRT_BUILD_FORCE_BVH2 | VKRT_BUILD_FORCE_BVH4))
     return fail(ctx, VKRT_ERR_INVALID, "scene_commit: unknown build flags");
   build_mode &= VKRT_BUILD_MODE_MASK;
-  if(build_mode < VKRT_BUILD_LBVH || build_mode > VKRT_BUILD_PLOC)
+  if(build_mode < VKRT_BUILD_LBVH || build_mode > VKRT_BUILD_SAH_GPU)
     return fail(ctx, VKRT_ERR_INVALID, "scene_commit: unknown build mode");
   cudaSetDevice(ctx->device);
   syncAll(ctx);
@@ -1142,6 +1143,20 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
     wf.numLocalPixels = nLocal;
     wf.pixelOfLocal   = dPix;
     uint32_t* sortAlt = ctx->sortQueueAlt;  // third queue buffer of the optional ray sort (rotates with queueCur)
+    // Bounce from which the fused tail kernel takes over (vkrt_render_opts.tail_from, else VKRT_TAIL_FROM: 0 never, n > 0 from bounce n; default: from bounce 3
+    // for small wavefronts -- an interactive frame, a thin multi-GPU shard -- where launch gaps and kernel tails outweigh the
+    // less efficient one-thread-per-path traversal; large batches keep one launch per stage).  Same image either way.
+    static const int tailEnv = []() { const char* e = getenv("VKRT_TAIL_FROM"); return e ? atoi(e) : -1; }();
+    static const long long tailAutoPaths = []() { const char* e = getenv("VKRT_TAIL_AUTO_PATHS"); return e ? atoll(e) : (long long)(9u << 20); }();
+    int tailFrom = 1 << 30;
+    if(!counting && !heatmap && !o.sort_rays)
+    {
+      const int want = o.tail_from != 0 ? o.tail_from : (tailEnv == 0 ? -1 : (tailEnv > 0 ? tailEnv : 0));  // options, then environment
+      if(want > 0)
+        tailFrom = want;
+      else if(want == 0 && (long long)wf.numPaths <= tailAutoPaths)
+        tailFrom = 3;
+    }
     FrameParams fp{};
     fp.state         = *state;
     fp.state.frame   = state->frame + done;
@@ -1160,6 +1175,19 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
       {
         fp.depth      = depth;
         wf.shadowSlot = (uint32_t)(depth & 1);
+        if(depth >= tailFrom)
+        {
+          // fused tail: every remaining bounce of the few paths still alive in one launch (tailKernel, vkrt_shade.cu)
+          if(overlap && depth > 0)
+            ev(cudaStreamWaitEvent(st, sl.evShadow, 0));  // the radiance the previous bounce's shadow rays resolve into
+          ScopedTimer t(ctx, timing, T_TAIL);
+          if(o.precise_shading)
+            launchTailPrecise(st, ctx->view, wf, fp, dstats, ctx->numSMs);
+          else
+            launchTailFast(st, ctx->view, wf, fp, dstats, ctx->numSMs);
+          ctx->stats.kernel_launches++;
+          break;
+        }
         if(o.sort_rays && depth >= 1)
         {
           // order this bounce's queue by (direction octant, origin Morton code); the live count is read back (one host

@@ -80,6 +80,9 @@ void launchRaygen(cudaStream_t s, const SceneView& scene, const Wavefront& wf, c
 // vkrt_shade.cu is compiled twice: IEEE-exact arithmetic, and approximate division / sqrt / SFU transcendentals (the default)
 void launchShadePrecise(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs);
 void launchShadeFast(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs);
+// fused tail (vkrt_shade.cu): every remaining bounce from fp.depth on, one thread per live path
+void launchTailPrecise(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs);
+void launchTailFast(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs);
 void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, int numSMs);
 void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, int numSMs);
 void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats, bool primary);

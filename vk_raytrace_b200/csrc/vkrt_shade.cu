@@ -15,6 +15,7 @@
 #include "vkrt_texture.cuh"
 #include "vkrt_bsdf.cuh"
 #include "vkrt_sunsky.cuh"
+#include "vkrt_traverse.cuh"
 #include "vkrt_internal.h"
 
 namespace vkrt {
@@ -562,6 +563,73 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(cons
     atomicAdd(&stats->closestRays, (unsigned long long)count);
 }
 
+// ---- fused tail: the thin late bounces of a wavefront in ONE launch -------------------------------------------------------------
+// From bounce `fp.depth` on, a path runs its own loop -- closest hit, the three shading phases, the shadow ray, the next bounce --
+// like the reference's megakernel (pathtrace.glsl:193-343).  After three bounces a few percent of the paths are alive, and three
+// launches per bounce cost more in launch gaps and kernel tails than in work (round 1: an interactive frame ran at half the
+// batched rate).  Draw order, arithmetic and accumulation order are those of the wavefront kernels: images are bit-identical.
+template <int PBR, int FM>
+__global__ void __launch_bounds__(128) tailKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
+                                                  const __grid_constant__ FrameParams fp0, TraceStats* stats)
+{
+  const uint32_t     count = wf.counters[0];
+  unsigned long long nClosest = 0, nShadow = 0;
+  for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+  {
+    const uint32_t p  = wf.queueCur[i];
+    const float4   ro = wf.rayO[p], rd = wf.rayD[p], t4 = wf.thr[p], r4 = wf.rad[p], a4 = wf.absb[p];
+    float3         o = f3(ro), d = f3(rd);
+    uint32_t       raySeed = __float_as_uint(rd.w);
+    BounceState    b;
+    b.throughput = f3(t4); b.radiance = f3(r4); b.absorption = f3(a4);
+    b.seed       = __float_as_uint(t4.w);
+    FrameParams fp = fp0;
+    for(int depth = fp0.depth; depth < fp0.state.maxDepth; depth++)
+    {
+      fp.depth = depth;
+      const TailHit h = traceSingle<false>(sc, o, d, kInfinity, raySeed);
+      nClosest++;
+      if(sc.hasNonOpaque)
+        pcg(b.seed);  // the one draw of ClosestHit (see alphaDraw)
+      b.rayD = d;
+      const float4 hit = (h.tri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(h.t, h.u, h.v, __uint_as_float(h.tri));
+      if(!bouncePhaseSurface(sc, fp, hit, b))
+        break;
+      bouncePhaseLight<PBR>(sc, fp, b);
+      ShadeOut out;
+      out.wantNext = out.wantShadow = false;
+      bouncePhaseSample<PBR>(sc, fp, b, out);
+      if(out.wantShadow)
+      {
+        nShadow++;
+        const TailHit s = traceSingle<true>(sc, out.shO, out.shD, out.shTmax, out.shSeed);
+        if(s.tri == ~0u)
+          b.radiance = b.radiance + out.shC;  // the any-hit kernel's `rad += contribution`, same operand order
+      }
+      if(!out.wantNext)
+        break;
+      o = out.nextO; d = out.nextD; raySeed = b.seed;
+    }
+    wf.thr[p]  = f4(b.throughput, __uint_as_float(b.seed));
+    wf.rad[p]  = f4(b.radiance, 0.f);
+    wf.absb[p] = f4(b.absorption, 0.f);
+  }
+  if(stats)
+  {
+#pragma unroll
+    for(int o = 16; o > 0; o >>= 1)
+    {
+      nClosest += __shfl_xor_sync(0xffffffffu, nClosest, o);
+      nShadow += __shfl_xor_sync(0xffffffffu, nShadow, o);
+    }
+    if((threadIdx.x & 31u) == 0 && (nClosest | nShadow))
+    {
+      atomicAdd(&stats->closestRays, nClosest);
+      atomicAdd(&stats->shadowRays, nShadow);
+    }
+  }
+}
+
 #ifndef VKRT_FAST_MATH
 // After the shadow pass of a bounce: next -> cur, reset cursors, count shadow rays.
 __global__ void swapQueuesKernel(Wavefront wf, TraceStats* stats, bool primary)
@@ -772,9 +840,11 @@ __global__ void __launch_bounds__(256) tonemapKernel(const float4* __restrict__ 
 #ifdef VKRT_FAST_MATH
 #define VKRT_SHADE_FM 1
 #define VKRT_LAUNCH_SHADE launchShadeFast
+#define VKRT_LAUNCH_TAIL launchTailFast
 #else
 #define VKRT_SHADE_FM 0
 #define VKRT_LAUNCH_SHADE launchShadePrecise
+#define VKRT_LAUNCH_TAIL launchTailPrecise
 void launchRaygen(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, int)
 {
   raygenKernel<<<(wf.numPaths + 255) / 256, 256, 0, s>>>(scene, wf, fp);
@@ -802,6 +872,24 @@ void VKRT_LAUNCH_SHADE(cudaStream_t s, const SceneView& scene, const Wavefront& 
     launchShadeT<0>(s, scene, wf, fp, stats, numSMs);
   else
     launchShadeT<1>(s, scene, wf, fp, stats, numSMs);
+}
+template <int PBR>
+static void launchTailT(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs)
+{
+  static int perSM = 0;
+  if(!perSM)
+  {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, tailKernel<PBR, VKRT_SHADE_FM>, 128, 0);
+    if(perSM < 1) perSM = 1;
+  }
+  tailKernel<PBR, VKRT_SHADE_FM><<<numSMs * perSM, 128, 0, s>>>(scene, wf, fp, stats);
+}
+void VKRT_LAUNCH_TAIL(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs)
+{
+  if(fp.state.pbrMode == 0)
+    launchTailT<0>(s, scene, wf, fp, stats, numSMs);
+  else
+    launchTailT<1>(s, scene, wf, fp, stats, numSMs);
 }
 #ifndef VKRT_FAST_MATH
 void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats, bool primary) { swapQueuesKernel<<<1, 1, 0, s>>>(wf, stats, primary); }

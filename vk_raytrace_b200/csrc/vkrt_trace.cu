@@ -46,8 +46,12 @@ namespace vkrt {
 #ifndef VKRT_TRACE_BLOCK
 #define VKRT_TRACE_BLOCK 128
 #endif
+#ifndef VKRT_LEAF_STREAM
+#define VKRT_LEAF_STREAM 1  // 0: one parked leaf per pass of the leaf loop (round 1)
+#endif
 #ifndef VKRT_BRANCHFREE
-#define VKRT_BRANCHFREE 1  // 0: the branchy push / pop / park of round 1 (A/B builds)
+#define VKRT_BRANCHFREE 0  // 1: branch-free push / pop / park (selects over the two topmost stack entries).  Measured on B200 (gpurun_out/bench_r02a_*):
+                           // 15 % fewer issue slots but a longer dependent chain per step -> closest-hit 19.96 vs 19.05 ms per 32 frames: off
 #endif
 constexpr int      kTraceBlock       = VKRT_TRACE_BLOCK;
 constexpr int      kStackShared      = VKRT_STACK_SHARED;  // entries per thread in shared memory
@@ -389,6 +393,71 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
         }
 
         // ---- parked leaves ---------------------------------------------------------------
+#if VKRT_LEAF_STREAM
+        // One loop over the triangles of the parked leaf and, right behind them, of a second leaf the lane found while it kept
+        // descending (node then holds that leaf's code): the warp iterates max(cnt1 + cnt2) times instead of max(cnt1) + max(cnt2)
+        // (ncu, round 1: 7.7 of 32 lanes active in this loop for incoherent rays -- leaves hold 1..8 triangles).
+        if(leaf != 0)
+        {
+          uint32_t cur = leaf & kLeafMask, end = cur + ((leaf >> kLeafCntSh) & 7u) + 1u;
+          for(;;)
+          {
+            if(cur == end)
+            {
+              if(!(node & kLeafBit))
+                break;
+              leaf = node;
+              node = pop();
+              cur  = leaf & kLeafMask;
+              end  = cur + ((leaf >> kLeafCntSh) & 7u) + 1u;
+            }
+            const float4 q0 = __ldg(&tris[3ull * cur + 0]);
+            const float4 q1 = __ldg(&tris[3ull * cur + 1]);
+            const float4 q2 = __ldg(&tris[3ull * cur + 2]);
+            cur++;
+            if(COUNT) nTris++;
+            const uint32_t flags = __float_as_uint(q0.w);
+            const uint32_t triId = __float_as_uint(q1.w);
+            // Moller-Trumbore, pinned operation order (no FMA: -fmad=false)
+            const float3 v0  = f3(q0);
+            const float3 e1  = f3(q1) - v0;
+            const float3 e2  = f3(q2) - v0;
+            const float3 p   = cross(d, e2);
+            const float  det = dot(e1, p);
+            if(!(flags & TRI_CULL_DISABLE))
+            {
+              const bool front = (flags & TRI_FLIP_FACING) ? (det < 0.0f) : (det > 0.0f);
+              if(!front)
+                continue;
+            }
+            if(det == 0.0f || !(det == det))
+              continue;
+            const float  inv = 1.0f / det;
+            const float3 tv  = o - v0;
+            const float  u   = dot(tv, p) * inv;
+            if(!(u >= 0.0f && u <= 1.0f))
+              continue;
+            const float3 q = cross(tv, e1);
+            const float  v = dot(d, q) * inv;
+            if(!(v >= 0.0f && (u + v) <= 1.0f))
+              continue;
+            const float t = dot(e2, q) * inv;
+            // t in (0, tmax): bestT starts at tmax, so only the tie branch has to exclude "no hit yet"
+            if(!(t > 0.0f && (t < bestT || (t == bestT && bestTri != ~0u && triId < bestTri))))
+              continue;
+            if(!(flags & TRI_OPAQUE) && !alphaTestPasses(sc, triId, __float_as_uint(q2.w), u, v, __float_as_uint(L.rayD[slot].w)))
+              continue;
+            bestT = t; bestU = u; bestV = v; bestTri = triId;
+            if(MODE != MODE_CLOSEST)
+            {
+              node = kDone;  // TerminateOnFirstHit
+              sp   = 0;
+              break;
+            }
+          }
+          leaf = 0;
+        }
+#else
         while(leaf != 0)
         {
           const uint32_t first = leaf & kLeafMask;
@@ -451,6 +520,8 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
             node = kDone;
           }
         }
+
+#endif
 
         // ---- dynamic fetch: leave to refill when the warp has thinned out ------------------------
         if(!exhausted && __popc(__activemask()) < kRefetchThreshold)

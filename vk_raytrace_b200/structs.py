@@ -35,7 +35,7 @@ class SunAndSky(C.Structure):
 
 class RenderOpts(C.Structure):
     _fields_ = [("seed_mode", i32), ("frames_in_flight", i32), ("tile_size", i32), ("shard_rank", i32), ("shard_count", i32),
-                ("count_traversal", i32), ("sort_rays", i32), ("profile", i32), ("precise_shading", i32), ("reserved", i32 * 7)]
+                ("count_traversal", i32), ("sort_rays", i32), ("profile", i32), ("precise_shading", i32), ("tail_from", i32), ("reserved", i32 * 6)]
 
 
 class Stats(C.Structure):
@@ -45,7 +45,7 @@ class Stats(C.Structure):
                 ("ms_accumulate", C.c_double), ("ms_tonemap", C.c_double), ("ms_build", C.c_double), ("num_triangles", u32),
                 ("num_bvh_nodes", u32), ("num_instances", u32), ("has_non_opaque", u32), ("shadow_nodes_visited", C.c_uint64),
                 ("shadow_tris_tested", C.c_uint64), ("bvh_max_depth", u32), ("node_bytes", u32), ("bvh_width", u32), ("_pad", u32), ("ms_trace_closest_primary", C.c_double),
-                ("ms_trace_shadow_primary", C.c_double), ("shadow_rays_primary", C.c_uint64), ("reserved", C.c_double * 1)]
+                ("ms_trace_shadow_primary", C.c_double), ("shadow_rays_primary", C.c_uint64), ("ms_tail", C.c_double)]
 
 
 # numpy dtypes for the bulk arrays (packed, identical to the C structs)
