@@ -347,6 +347,16 @@ int vkrt_create(int cuda_device, vkrt_ctx** out_ctx)
     return VKRT_ERR_CUDA;
   }
   ctx->stream = ctx->slots[0].s;
+  {
+    // the acceleration-structure build takes its temporaries from the stream-ordered pool: keep up to 1 GB of it warm between builds
+    cudaMemPool_t pool = nullptr;
+    if(cudaDeviceGetDefaultMemPool(&pool, cuda_device) == cudaSuccess && pool)
+    {
+      uint64_t keep = 1ull << 30;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   cudaDeviceGetAttribute(&ctx->numSMs, cudaDevAttrMultiProcessorCount, cuda_device);
   if(cudaMalloc(&ctx->dStats, sizeof(TraceStats)) != cudaSuccess)
   {

@@ -162,39 +162,44 @@ struct SahSlot
   uint32_t childBase;  // slots of the next level (left, right) when split
   int32_t  axis, bin;  // axis < 0: closed
   uint32_t finalIdx;   // closed: index into the closed-node boxes
-  uint32_t _pad;
+  int32_t  binIdx;     // open (count > stop): its block of 3 x 32 bins this level; -1: will be closed without a look at the bins
 };
 struct SahBin
 {
   uint32_t count;
   uint32_t lo[3], hi[3];  // ordered uints
 };
-
-__global__ void sahInitSlotsKernel(SahSlot* slots, uint32_t n)
+struct SahLevel
 {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= n)
-    return;
-  SahSlot s;
-  s.cb[0] = s.cb[1] = s.cb[2] = 0xffffffffu;
-  s.cb[3] = s.cb[4] = s.cb[5] = 0u;
-  s.count = 0; s.childBase = 0; s.axis = -1; s.bin = 0; s.finalIdx = 0; s._pad = 0;
-  slots[i] = s;
-}
-__global__ void sahRootKernel(SahSlot* slots, const uint32_t* __restrict__ boundsOrdered, uint32_t numTris)
+  uint32_t numSlots, numOpen;
+};
+
+__global__ void sahRootKernel(SahSlot* slots, const uint32_t* __restrict__ boundsOrdered, uint32_t numTris, SahLevel* levels, uint32_t* finalCount,
+                              uint32_t stop)
 {
   SahSlot s;
   for(int k = 0; k < 6; k++) s.cb[k] = boundsOrdered[k];
-  s.count = numTris; s.childBase = 0; s.axis = -1; s.bin = 0; s.finalIdx = 0; s._pad = 0;
+  s.count = numTris; s.childBase = 0; s.axis = -1; s.bin = 0; s.finalIdx = 0;
+  s.binIdx = numTris > stop ? 0 : -1;
   slots[0] = s;
+  for(int l = 0; l <= kSahPathBits + 1; l++) { levels[l].numSlots = 0; levels[l].numOpen = 0; }
+  levels[0].numSlots = 1;
+  levels[0].numOpen  = numTris > stop ? 1u : 0u;
+  *finalCount = 0;
 }
 
-__global__ void sahBinInitKernel(SahBin* bins, uint32_t n)
+// bins of the open nodes of this level: count 0, boxes inverted
+__global__ void sahBinClearKernel(SahBin* bins, const SahLevel* __restrict__ level)
 {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= n)
-    return;
-  bins[i].lo[0] = bins[i].lo[1] = bins[i].lo[2] = 0xffffffffu;  // count and hi[] were zeroed by the memset
+  const size_t n = (size_t)level->numOpen * 3 * kSahBins;
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+  {
+    SahBin b;
+    b.count = 0;
+    b.lo[0] = b.lo[1] = b.lo[2] = 0xffffffffu;
+    b.hi[0] = b.hi[1] = b.hi[2] = 0u;
+    bins[i] = b;
+  }
 }
 
 __device__ __forceinline__ void triBoundsCentroid(const float4* __restrict__ wtri, uint32_t i, float (&lo)[3], float (&hi)[3], float (&c)[3])
@@ -211,7 +216,7 @@ __device__ __forceinline__ int sahBinOf(float c, float cmin, float cmax)
 }
 
 __global__ void sahBinKernel(const float4* __restrict__ wtri, uint32_t numTris, const int32_t* __restrict__ triSlot, const SahSlot* __restrict__ slots,
-                             SahBin* __restrict__ bins, uint32_t stop)
+                             SahBin* __restrict__ bins)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if(i >= numTris)
@@ -220,7 +225,7 @@ __global__ void sahBinKernel(const float4* __restrict__ wtri, uint32_t numTris, 
   if(sidx < 0)
     return;
   const SahSlot& S = slots[sidx];
-  if(S.count <= stop)
+  if(S.binIdx < 0)
     return;  // will be closed: no split to evaluate
   float lo[3], hi[3], c[3];
   triBoundsCentroid(wtri, i, lo, hi, c);
@@ -233,7 +238,7 @@ __global__ void sahBinKernel(const float4* __restrict__ wtri, uint32_t numTris, 
       continue;
     // warp-aggregated: neighbouring triangles of a mesh mostly fall into the same bin of the same node, and near the root every
     // triangle of the scene hits the same 96 bins -- lanes with the same target combine (match + reduce) and one of them does the atomics
-    const uint32_t key = (uint32_t)(((size_t)sidx * 3 + a) * kSahBins + sahBinOf(c[a], cmin, cmax));
+    const uint32_t key = (uint32_t)(((size_t)S.binIdx * 3 + a) * kSahBins + sahBinOf(c[a], cmin, cmax));
     const unsigned m   = __match_any_sync(__activemask(), key);
     const uint32_t l0 = __reduce_min_sync(m, olo[0]), l1 = __reduce_min_sync(m, olo[1]), l2 = __reduce_min_sync(m, olo[2]);
     const uint32_t h0 = __reduce_max_sync(m, ohi[0]), h1 = __reduce_max_sync(m, ohi[1]), h2 = __reduce_max_sync(m, ohi[2]);
@@ -253,27 +258,27 @@ __device__ __forceinline__ float sahArea(const float (&lo)[3], const float (&hi)
   return 2.0f * (x * y + y * z + z * x);
 }
 
-// one warp per open node, lane = bin
-__global__ void sahSplitKernel(SahSlot* __restrict__ slots, uint32_t numSlots, const SahBin* __restrict__ bins, SahSlot* __restrict__ next,
-                               uint32_t* __restrict__ nextCount, Box* __restrict__ finals, uint32_t* __restrict__ finalCount, uint32_t stop, int lastLevel)
+// one warp per node of this level, lane = bin
+__global__ void sahSplitKernel(SahSlot* __restrict__ slots, SahLevel* __restrict__ levels, int L, const SahBin* __restrict__ bins,
+                               SahSlot* __restrict__ next, Box* __restrict__ finals, uint32_t* __restrict__ finalCount, uint32_t stop, uint32_t maxSlots)
 {
   const uint32_t sidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int      lane = threadIdx.x & 31;
-  if(sidx >= numSlots)
+  if(sidx >= levels[L].numSlots)
     return;
-  SahSlot S = slots[sidx];
-  float   bestCost = 3e38f;
-  int     bestAxis = -1, bestBin = -1;
+  SahSlot  S = slots[sidx];
+  float    bestCost = 3e38f;
+  int      bestAxis = -1, bestBin = -1;
   uint32_t bestL = 0;
-  float   nodeArea = 0.f;
-  if(S.count > stop && !lastLevel)
+  float    nodeArea = 0.f;
+  if(S.binIdx >= 0)
   {
     for(int a = 0; a < 3; a++)
     {
       const float cmin = floatFromOrdered(S.cb[a]), cmax = floatFromOrdered(S.cb[3 + a]);
       if(!(cmax > cmin))
         continue;
-      const SahBin b = bins[((size_t)sidx * 3 + a) * kSahBins + lane];
+      const SahBin b = bins[((size_t)S.binIdx * 3 + a) * kSahBins + lane];
       // inclusive prefix (left) and suffix (right) unions over the lanes
       float    llo[3], lhi[3], rlo[3], rhi[3];
       uint32_t lc = b.count, rc = b.count;
@@ -317,10 +322,9 @@ __global__ void sahSplitKernel(SahSlot* __restrict__ slots, uint32_t numSlots, c
       if(lane < 31 && lc > 0 && rcn > 0)
         cost = sahArea(llo, lhi) * (float)lc + sahArea(nlo, nhi) * (float)rcn;
       // the node's own box: prefix of the last lane
-      float full[6];
-      for(int k = 0; k < 3; k++) { full[k] = __shfl_sync(0xffffffffu, llo[k], 31); full[3 + k] = __shfl_sync(0xffffffffu, lhi[k], 31); }
       {
-        const float flo[3] = {full[0], full[1], full[2]}, fhi[3] = {full[3], full[4], full[5]};
+        float flo[3], fhi[3];
+        for(int k = 0; k < 3; k++) { flo[k] = __shfl_sync(0xffffffffu, llo[k], 31); fhi[k] = __shfl_sync(0xffffffffu, lhi[k], 31); }
         nodeArea = sahArea(flo, fhi);
       }
       // warp argmin, ties to the lower bin; axes are visited in order, strict improvement only (as the host builder)
@@ -344,12 +348,27 @@ __global__ void sahSplitKernel(SahSlot* __restrict__ slots, uint32_t numSlots, c
   bool split = bestAxis >= 0;
   if(split && S.count <= 4u && nodeArea * (float)S.count <= nodeArea + bestCost)
     split = false;
+  uint32_t base = 0;
   if(split)
   {
-    const uint32_t base = atomicAdd(nextCount, 2u);
+    base = atomicAdd(&levels[L + 1].numSlots, 2u);
+    if(base + 2u > maxSlots)
+      split = false;  // cannot happen for counts that add up (children of open nodes only); keeps a corrupt input from writing out of bounds
+  }
+  if(split)
+  {
     S.childBase = base; S.axis = bestAxis; S.bin = bestBin;
-    next[base].count     = bestL;
-    next[base + 1].count = S.count - bestL;
+    const bool     nextIsLast = (L + 1) >= kSahPathBits;
+    const uint32_t cnt[2]     = {bestL, S.count - bestL};
+    for(int k = 0; k < 2; k++)
+    {
+      SahSlot ch;
+      ch.cb[0] = ch.cb[1] = ch.cb[2] = 0xffffffffu;
+      ch.cb[3] = ch.cb[4] = ch.cb[5] = 0u;
+      ch.count = cnt[k]; ch.childBase = 0; ch.axis = -1; ch.bin = 0; ch.finalIdx = 0;
+      ch.binIdx = (cnt[k] > stop && !nextIsLast) ? (int32_t)atomicAdd(&levels[L + 1].numOpen, 1u) : -1;
+      next[base + k] = ch;
+    }
   }
   else
   {
@@ -508,7 +527,7 @@ __global__ void refitKernel(const float4* __restrict__ wtri, const uint32_t* __r
                             const int2* __restrict__ children, const int* __restrict__ parentInner, const int* __restrict__ parentLeaf,
                             Box* __restrict__ leafBox, Box* __restrict__ nodeBox, float* __restrict__ nodeCost, int* __restrict__ nodeDepth,
                             uint32_t* __restrict__ collapsed, const int2* __restrict__ ranges, int* __restrict__ flags, int collapseMax,
-                            int* __restrict__ maxDepthOut)
+                            int* __restrict__ maxDepthOut, const uint64_t* __restrict__ groupKeys = nullptr)
 {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if(j >= n)
@@ -522,7 +541,10 @@ __global__ void refitKernel(const float4* __restrict__ wtri, const uint32_t* __r
   leafBox[j] = bx;
   if(n == 1)
     return;
-  const float Ct = 1.0f, Ci = 1.2f;
+  // groupKeys (VKRT_BUILD_SAH_GPU): sorted path-code keys.  Triangles with the same path code are one closed node of the SAH
+  // build; only inside such a group may a leaf be formed (with the host builder's rule: a leaf when splitting does not pay,
+  // inner-node cost 1.0), across groups the SAH split stands.
+  const float Ct = 1.0f, Ci = groupKeys ? 1.0f : 1.2f;
   int node = parentLeaf[j];
   __threadfence();
   while(node >= 0)
@@ -551,6 +573,8 @@ __global__ void refitKernel(const float4* __restrict__ wtri, const uint32_t* __r
     float cInner = Ci * A + cl + cr;
     float cLeaf  = Ct * A * (float)count;
     bool  col    = collapseMax > 1 && count <= collapseMax && cLeaf <= cInner;
+    if(groupKeys)
+      col = col && ((groupKeys[rg.x] >> 33) == (groupKeys[rg.y] >> 33));
     collapsed[node] = col ? 1u : 0u;
     nodeCost[node]  = col ? cLeaf : cInner;
     int depth       = col ? 0 : (max(dl, dr) + 1);
@@ -800,6 +824,20 @@ __global__ void emptySceneKernel(float4* nodes)
       goto fail;                                                                                                       \
     }                                                                                                                  \
   } while(0)
+#define TCK(x) CK(x)
+// Build temporaries come from CUDA's stream-ordered pool (the context keeps up to 1 GB of it warm, vkrt_create): a build is ~40
+// allocations, and plain cudaMalloc / cudaFree (synchronising, tens of microseconds to milliseconds each) cost more than the kernels.
+template <class T>
+static cudaError_t tmpAlloc(T** p, size_t bytes, cudaStream_t s)
+{
+  return cudaMallocAsync(reinterpret_cast<void**>(p), bytes ? bytes : 16, s);
+}
+static void tmpFree(void* p, cudaStream_t s)
+{
+  if(p)
+    cudaFreeAsync(p, s);
+}
+
 
 // 32-byte nodes (VKRT_NODE_FORMAT=q32, and the box encoding of the 4-wide tree): a node that fits one 256-bit load.  On an
 // L2-resident BVH it is no faster than the 64-byte node (the step is latency bound, profiles/README.md); it halves the
@@ -998,8 +1036,8 @@ bool collapseBvhWide(cudaStream_t stream, BvhResult& bvh, std::string& err, uint
   cudaFree(bvh.wnodes);
   bvh.wnodes = nullptr;
   CK(cudaMalloc(&bvh.wnodes, 64ull * n));
-  CK(cudaMalloc(&src, 4ull * n));
-  CK(cudaMalloc(&count, 4));
+  CK(tmpAlloc(&src, 4ull * n, stream));
+  CK(tmpAlloc(&count, 4, stream));
   CK(cudaMemsetAsync(src, 0, 4, stream));  // the root of the binary tree is node 0
   {
     const uint32_t one = 1;
@@ -1023,10 +1061,10 @@ bool collapseBvhWide(cudaStream_t stream, BvhResult& bvh, std::string& err, uint
   }
   bvh.numWideNodes = end;
   bvh.wideDepth    = (int)levels;
-  cudaFree(src); cudaFree(count);
+  tmpFree(src, stream); tmpFree(count, stream);
   return true;
 fail:
-  cudaFree(src); cudaFree(count); cudaFree(bvh.wnodes);
+  tmpFree(src, stream); tmpFree(count, stream); cudaFree(bvh.wnodes);
   bvh.wnodes = nullptr;
   return false;
 }
@@ -1043,13 +1081,13 @@ static bool plocTopology(cudaStream_t stream, const float4* wtri, const uint32_t
   size_t    scanBytes = 0;
   const int B = 256;
   int       c = n, rounds = 0, forcePair = 0;
-  CK(cudaMalloc(&cid, 4ull * n)); CK(cudaMalloc(&cidT, 4ull * n)); CK(cudaMalloc(&csize, 4ull * n)); CK(cudaMalloc(&csizeT, 4ull * n));
-  CK(cudaMalloc(&nn, 4ull * n)); CK(cudaMalloc(&nodeSize, 4ull * n)); CK(cudaMalloc(&counters, 8));
-  CK(cudaMalloc(&leafPos, 4ull * n)); CK(cudaMalloc(&parentLeafOld, 4ull * n));
-  CK(cudaMalloc(&cbox, sizeof(Box) * (size_t)n)); CK(cudaMalloc(&cboxT, sizeof(Box) * (size_t)n));
-  CK(cudaMalloc(&valid, 4ull * n)); CK(cudaMalloc(&pos, 4ull * n));
+  CK(tmpAlloc(&cid, 4ull * n, stream)); CK(tmpAlloc(&cidT, 4ull * n, stream)); CK(tmpAlloc(&csize, 4ull * n, stream)); CK(tmpAlloc(&csizeT, 4ull * n, stream));
+  CK(tmpAlloc(&nn, 4ull * n, stream)); CK(tmpAlloc(&nodeSize, 4ull * n, stream)); CK(tmpAlloc(&counters, 8, stream));
+  CK(tmpAlloc(&leafPos, 4ull * n, stream)); CK(tmpAlloc(&parentLeafOld, 4ull * n, stream));
+  CK(tmpAlloc(&cbox, sizeof(Box) * (size_t)n, stream)); CK(tmpAlloc(&cboxT, sizeof(Box) * (size_t)n, stream));
+  CK(tmpAlloc(&valid, 4ull * n, stream)); CK(tmpAlloc(&pos, 4ull * n, stream));
   CK(cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, valid, pos, n, stream));
-  CK(cudaMalloc(&scanTemp, scanBytes ? scanBytes : 16));
+  CK(tmpAlloc(&scanTemp, scanBytes ? scanBytes : 16, stream));
   CK(cudaMemsetAsync(counters, 0, 8, stream));
   plocInitKernel<<<(n + B - 1) / B, B, 0, stream>>>(wtri, sortedVals, n, cid, cbox, csize);
   if(launches) (*launches)++;
@@ -1086,81 +1124,70 @@ static bool plocTopology(cudaStream_t stream, const float4* wtri, const uint32_t
     CK(cudaStreamSynchronize(stream));
   }
   if(roundsOut) *roundsOut = rounds;
-  cudaFree(cid); cudaFree(cidT); cudaFree(csize); cudaFree(csizeT); cudaFree(nn); cudaFree(nodeSize); cudaFree(counters);
-  cudaFree(leafPos); cudaFree(parentLeafOld); cudaFree(cbox); cudaFree(cboxT); cudaFree(valid); cudaFree(pos); cudaFree(scanTemp);
+  tmpFree(cid, stream); tmpFree(cidT, stream); tmpFree(csize, stream); tmpFree(csizeT, stream); tmpFree(nn, stream); tmpFree(nodeSize, stream); tmpFree(counters, stream);
+  tmpFree(leafPos, stream); tmpFree(parentLeafOld, stream); tmpFree(cbox, stream); tmpFree(cboxT, stream); tmpFree(valid, stream); tmpFree(pos, stream); tmpFree(scanTemp, stream);
   return true;
 fail:
-  cudaFree(cid); cudaFree(cidT); cudaFree(csize); cudaFree(csizeT); cudaFree(nn); cudaFree(nodeSize); cudaFree(counters);
-  cudaFree(leafPos); cudaFree(parentLeafOld); cudaFree(cbox); cudaFree(cboxT); cudaFree(valid); cudaFree(pos); cudaFree(scanTemp);
+  tmpFree(cid, stream); tmpFree(cidT, stream); tmpFree(csize, stream); tmpFree(csizeT, stream); tmpFree(nn, stream); tmpFree(nodeSize, stream); tmpFree(counters, stream);
+  tmpFree(leafPos, stream); tmpFree(parentLeafOld, stream); tmpFree(cbox, stream); tmpFree(cboxT, stream); tmpFree(valid, stream); tmpFree(pos, stream); tmpFree(scanTemp, stream);
   return false;
 }
 
-// Path-code keys of the GPU binned-SAH build (see 2b): fills keys / vals like mortonKernel.
+// Path-code keys of the GPU binned-SAH build (see 2b): fills keys / vals like mortonKernel.  No host synchronisation: every
+// level is launched unconditionally (kSahPathBits + 1 of them; the node counts live on the device, levels past the real depth of the
+// tree find nothing to do) and the temporaries come from the stream-ordered pool.
 static bool sahPathKeys(cudaStream_t stream, const float4* wtri, uint32_t n, const uint32_t* boundsOrdered, uint64_t* keys, uint32_t* vals,
-                        std::string& err, uint64_t* launches, int* levelsOut)
+                        std::string& err, uint64_t* launches)
 {
-  // nodes of <= stop triangles are closed (measured on the 263 k-triangle scene, closest + shadow ms per 32 frames: stop 4: 20.1 + 14.3,
-  // 8: 20.5 + 14.7, 16: 20.5 + 14.6 with 8-triangle leaves)
-  static const uint32_t stop = []() { const char* e = getenv("VKRT_SAH_STOP"); int v = e ? atoi(e) : 4; return (uint32_t)(v < 1 ? 1 : (v > 64 ? 64 : v)); }();
-  const uint32_t maxSlots = 2u * (n / (stop + 1u)) + 64u;  // open nodes hold > stop triangles each; their children at most twice as many
+  // nodes of <= stop triangles are closed without a look at the bins (measured on the 263 k-triangle scene, closest + shadow ms per 32
+  // frames: stop 2: 19.5 + 14.0 = the host builder's tree; 4: 19.9 + 14.3; 8: 20.3 + 14.5).  Huge scenes raise it so that the bins
+  // (2688 bytes per open node) stay below 2 GB.
+  static const uint32_t stopEnv = []() { const char* e = getenv("VKRT_SAH_STOP"); int v = e ? atoi(e) : 2; return (uint32_t)(v < 1 ? 1 : (v > 64 ? 64 : v)); }();
+  uint32_t stop = stopEnv;
+  while((size_t)(n / (stop + 1u) + 1u) * 3 * kSahBins * sizeof(SahBin) > ((size_t)2 << 30) && stop < 64u)
+    stop++;
+  const uint32_t maxOpen  = n / (stop + 1u) + 1u;  // open nodes hold > stop triangles each
+  const uint32_t maxSlots = 2u * maxOpen + 2u;     // ... and the nodes of a level are the children of the previous level's open nodes
   SahSlot *slotsA = nullptr, *slotsB = nullptr;
   SahBin*   bins = nullptr;
+  SahLevel* levels = nullptr;
   int32_t*  triSlot = nullptr;
-  uint32_t *triCode = nullptr, *triDepth = nullptr, *triFinal = nullptr, *counters = nullptr;
+  uint32_t *triCode = nullptr, *triDepth = nullptr, *triFinal = nullptr, *finalCount = nullptr;
   Box*      finals = nullptr;
   const int B = 256;
   const uint32_t grid = (n + B - 1) / B;
-  uint32_t  numSlots = 1;
-  int       level = 0;
-  CK(cudaMalloc(&slotsA, sizeof(SahSlot) * (size_t)maxSlots)); CK(cudaMalloc(&slotsB, sizeof(SahSlot) * (size_t)maxSlots));
-  CK(cudaMalloc(&bins, sizeof(SahBin) * (size_t)maxSlots * 3 * kSahBins));
-  CK(cudaMalloc(&triSlot, 4ull * n)); CK(cudaMalloc(&triCode, 4ull * n)); CK(cudaMalloc(&triDepth, 4ull * n)); CK(cudaMalloc(&triFinal, 4ull * n));
-  CK(cudaMalloc(&counters, 8)); CK(cudaMalloc(&finals, sizeof(Box) * (size_t)(n + 1)));
-  CK(cudaMemsetAsync(triSlot, 0, 4ull * n, stream)); CK(cudaMemsetAsync(triCode, 0, 4ull * n, stream));
-  CK(cudaMemsetAsync(triDepth, 0, 4ull * n, stream)); CK(cudaMemsetAsync(triFinal, 0, 4ull * n, stream));
-  CK(cudaMemsetAsync(counters, 0, 8, stream));
-  sahRootKernel<<<1, 1, 0, stream>>>(slotsA, boundsOrdered, n);
+  TCK(tmpAlloc(&slotsA, sizeof(SahSlot) * (size_t)maxSlots, stream)); TCK(tmpAlloc(&slotsB, sizeof(SahSlot) * (size_t)maxSlots, stream));
+  TCK(tmpAlloc(&bins, sizeof(SahBin) * (size_t)maxOpen * 3 * kSahBins, stream));
+  TCK(tmpAlloc(&levels, sizeof(SahLevel) * (kSahPathBits + 2), stream));
+  TCK(tmpAlloc(&triSlot, 4ull * n, stream)); TCK(tmpAlloc(&triCode, 4ull * n, stream)); TCK(tmpAlloc(&triDepth, 4ull * n, stream));
+  TCK(tmpAlloc(&triFinal, 4ull * n, stream));
+  TCK(tmpAlloc(&finalCount, 4, stream)); TCK(tmpAlloc(&finals, sizeof(Box) * (size_t)(n + 1), stream));
+  TCK(cudaMemsetAsync(triSlot, 0, 4ull * n, stream)); TCK(cudaMemsetAsync(triCode, 0, 4ull * n, stream));
+  TCK(cudaMemsetAsync(triDepth, 0, 4ull * n, stream)); TCK(cudaMemsetAsync(triFinal, 0, 4ull * n, stream));
+  sahRootKernel<<<1, 1, 0, stream>>>(slotsA, boundsOrdered, n, levels, finalCount, stop);
   if(launches) (*launches)++;
-  for(;; level++)
+  for(int level = 0; level <= kSahPathBits; level++)
   {
-    const int last = level >= kSahPathBits ? 1 : 0;
-    // bins of this level: count 0, boxes inverted (ordered-uint min = 0xffffffff, max = 0): two memsets over the used part
-    {
-      const size_t nb = (size_t)numSlots * 3 * kSahBins;
-      CK(cudaMemsetAsync(bins, 0, sizeof(SahBin) * nb, stream));
-    }
-    sahBinInitKernel<<<(unsigned)(((size_t)numSlots * 3 * kSahBins + B - 1) / B), B, 0, stream>>>(bins, (uint32_t)((size_t)numSlots * 3 * kSahBins));
-    if(!last)
-      sahBinKernel<<<grid, B, 0, stream>>>(wtri, n, triSlot, slotsA, bins, stop);
-    const uint32_t nextCap = std::min<uint32_t>(maxSlots, 2u * numSlots);
-    sahInitSlotsKernel<<<(nextCap + B - 1) / B, B, 0, stream>>>(slotsB, nextCap);
-    CK(cudaMemsetAsync(counters, 0, 4, stream));  // [0] next level's slot count; [1] closed nodes so far
-    sahSplitKernel<<<(unsigned)(((size_t)numSlots * 32 + B - 1) / B), B, 0, stream>>>(slotsA, numSlots, bins, slotsB, counters, finals, counters + 1, stop, last);
+    // upper bounds for the grids: 2^level nodes at most, never more than maxSlots
+    const uint32_t slotsBound = (level < 31 && (1u << level) < maxSlots) ? (1u << level) : maxSlots;
+    const uint32_t openBound  = std::min<uint32_t>(slotsBound, maxOpen);
+    const size_t   binBound   = (size_t)openBound * 3 * kSahBins;
+    sahBinClearKernel<<<(unsigned)std::min<size_t>((binBound + B - 1) / B, 148 * 16), B, 0, stream>>>(bins, levels + level);
+    sahBinKernel<<<grid, B, 0, stream>>>(wtri, n, triSlot, slotsA, bins);
+    sahSplitKernel<<<(unsigned)(((size_t)slotsBound * 32 + B - 1) / B), B, 0, stream>>>(slotsA, levels, level, bins, slotsB, finals, finalCount, stop, maxSlots);
     sahApplyKernel<<<grid, B, 0, stream>>>(wtri, n, triSlot, triCode, triDepth, triFinal, slotsA, slotsB);
-    if(launches) (*launches) += 5;
-    uint32_t next = 0;
-    CK(cudaMemcpyAsync(&next, counters, 4, cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    if(next == 0)
-      break;
-    if(next > maxSlots)
-    {
-      err = "sahPathKeys: slot count out of range";
-      goto fail;
-    }
-    numSlots = next;
+    if(launches) (*launches) += 4;
     std::swap(slotsA, slotsB);
   }
   sahKeyKernel<<<grid, B, 0, stream>>>(wtri, n, triCode, triDepth, triFinal, finals, keys, vals);
   if(launches) (*launches)++;
-  CK(cudaGetLastError());
-  if(levelsOut) *levelsOut = level + 1;
-  cudaFree(slotsA); cudaFree(slotsB); cudaFree(bins); cudaFree(triSlot); cudaFree(triCode); cudaFree(triDepth); cudaFree(triFinal);
-  cudaFree(counters); cudaFree(finals);
+  TCK(cudaGetLastError());
+  tmpFree(slotsA, stream); tmpFree(slotsB, stream); tmpFree(bins, stream); tmpFree(levels, stream); tmpFree(triSlot, stream); tmpFree(triCode, stream);
+  tmpFree(triDepth, stream); tmpFree(triFinal, stream); tmpFree(finalCount, stream); tmpFree(finals, stream);
   return true;
 fail:
-  cudaFree(slotsA); cudaFree(slotsB); cudaFree(bins); cudaFree(triSlot); cudaFree(triCode); cudaFree(triDepth); cudaFree(triFinal);
-  cudaFree(counters); cudaFree(finals);
+  tmpFree(slotsA, stream); tmpFree(slotsB, stream); tmpFree(bins, stream); tmpFree(levels, stream); tmpFree(triSlot, stream); tmpFree(triCode, stream);
+  tmpFree(triDepth, stream); tmpFree(triFinal, stream); tmpFree(finalCount, stream); tmpFree(finals, stream);
   return false;
 }
 
@@ -1199,15 +1226,15 @@ bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* d
   }
   {
     size_t n = numTris;
-    CK(cudaMalloc(&wtri, sizeof(float4) * 3 * n));
-    CK(cudaMalloc(&bounds, 6 * sizeof(uint32_t)));
-    CK(cudaMalloc(&keysA, 8 * n)); CK(cudaMalloc(&keysB, 8 * n));
-    CK(cudaMalloc(&valsA, 4 * n)); CK(cudaMalloc(&valsB, 4 * n));
-    CK(cudaMalloc(&children, sizeof(int2) * n)); CK(cudaMalloc(&ranges, sizeof(int2) * n));
-    CK(cudaMalloc(&parentInner, 4 * n)); CK(cudaMalloc(&parentLeaf, 4 * n)); CK(cudaMalloc(&flags, 4 * n));
-    CK(cudaMalloc(&nodeDepth, 4 * n)); CK(cudaMalloc(&maxDepthDev, 4));
-    CK(cudaMalloc(&leafBox, sizeof(Box) * n)); CK(cudaMalloc(&nodeBox, sizeof(Box) * n));
-    CK(cudaMalloc(&nodeCost, 4 * n)); CK(cudaMalloc(&collapsed, 4 * n));
+    CK(tmpAlloc(&wtri, sizeof(float4) * 3 * n, stream));
+    CK(tmpAlloc(&bounds, 6 * sizeof(uint32_t), stream));
+    CK(tmpAlloc(&keysA, 8 * n, stream)); CK(tmpAlloc(&keysB, 8 * n, stream));
+    CK(tmpAlloc(&valsA, 4 * n, stream)); CK(tmpAlloc(&valsB, 4 * n, stream));
+    CK(tmpAlloc(&children, sizeof(int2) * n, stream)); CK(tmpAlloc(&ranges, sizeof(int2) * n, stream));
+    CK(tmpAlloc(&parentInner, 4 * n, stream)); CK(tmpAlloc(&parentLeaf, 4 * n, stream)); CK(tmpAlloc(&flags, 4 * n, stream));
+    CK(tmpAlloc(&nodeDepth, 4 * n, stream)); CK(tmpAlloc(&maxDepthDev, 4, stream));
+    CK(tmpAlloc(&leafBox, sizeof(Box) * n, stream)); CK(tmpAlloc(&nodeBox, sizeof(Box) * n, stream));
+    CK(tmpAlloc(&nodeCost, 4 * n, stream)); CK(tmpAlloc(&collapsed, 4 * n, stream));
 
     uint32_t initB[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
     CK(cudaMemcpyAsync(bounds, initB, sizeof(initB), cudaMemcpyHostToDevice, stream));
@@ -1218,7 +1245,7 @@ bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* d
     flattenKernel<<<grid, B, 0, stream>>>(dInst, dInstTriOffset, numInst, dGeo, numTris, wtri, out.triInfo, out.triShade, bounds);
     if(buildMode == VKRT_BUILD_SAH_GPU && n > 1)
     {
-      if(!sahPathKeys(stream, wtri, numTris, bounds, keysA, valsA, err, launches, nullptr))
+      if(!sahPathKeys(stream, wtri, numTris, bounds, keysA, valsA, err, launches))
         goto fail;
     }
     else
@@ -1227,7 +1254,7 @@ bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* d
     cub::DoubleBuffer<uint64_t> dk(keysA, keysB);
     cub::DoubleBuffer<uint32_t> dv(valsA, valsB);
     CK(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, dk, dv, (int)n, 0, 63, stream));
-    CK(cudaMalloc(&cubTemp, tempBytes ? tempBytes : 16));
+    CK(tmpAlloc(&cubTemp, tempBytes ? tempBytes : 16, stream));
     CK(cub::DeviceRadixSort::SortPairs(cubTemp, tempBytes, dk, dv, (int)n, 0, 63, stream));
     const uint64_t* sk = dk.Current();
     const uint32_t* sv = dv.Current();
@@ -1249,21 +1276,22 @@ bool buildBvh(cudaStream_t stream, const InstanceXform* dInst, const uint32_t* d
       collapseMax = leafMax;
     }
     refitKernel<<<grid, B, 0, stream>>>(wtri, sv, (int)n, out.tris, children, parentInner, parentLeaf, leafBox, nodeBox, nodeCost,
-                                       nodeDepth, collapsed, ranges, flags, collapseMax, maxDepthDev);
+                                       nodeDepth, collapsed, ranges, flags, collapseMax, maxDepthDev,
+                                       (buildMode == VKRT_BUILD_SAH_GPU && n > 1) ? sk : nullptr);
     emitKernel<<<grid, B, 0, stream>>>((int)n, children, ranges, leafBox, nodeBox, collapsed, out.nodes);
     if(launches) (*launches) += 5 + 7;  // ours + the radix-sort passes of the library
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&out.maxDepth, maxDepthDev, 4, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
   }
-  cudaFree(wtri); cudaFree(bounds); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB); cudaFree(cubTemp);
-  cudaFree(children); cudaFree(ranges); cudaFree(parentInner); cudaFree(parentLeaf); cudaFree(flags); cudaFree(nodeDepth);
-  cudaFree(maxDepthDev); cudaFree(leafBox); cudaFree(nodeBox); cudaFree(nodeCost); cudaFree(collapsed);
+  tmpFree(wtri, stream); tmpFree(bounds, stream); tmpFree(keysA, stream); tmpFree(keysB, stream); tmpFree(valsA, stream); tmpFree(valsB, stream); tmpFree(cubTemp, stream);
+  tmpFree(children, stream); tmpFree(ranges, stream); tmpFree(parentInner, stream); tmpFree(parentLeaf, stream); tmpFree(flags, stream); tmpFree(nodeDepth, stream);
+  tmpFree(maxDepthDev, stream); tmpFree(leafBox, stream); tmpFree(nodeBox, stream); tmpFree(nodeCost, stream); tmpFree(collapsed, stream);
   return true;
 fail:
-  cudaFree(wtri); cudaFree(bounds); cudaFree(keysA); cudaFree(keysB); cudaFree(valsA); cudaFree(valsB); cudaFree(cubTemp);
-  cudaFree(children); cudaFree(ranges); cudaFree(parentInner); cudaFree(parentLeaf); cudaFree(flags); cudaFree(nodeDepth);
-  cudaFree(maxDepthDev); cudaFree(leafBox); cudaFree(nodeBox); cudaFree(nodeCost); cudaFree(collapsed);
+  tmpFree(wtri, stream); tmpFree(bounds, stream); tmpFree(keysA, stream); tmpFree(keysB, stream); tmpFree(valsA, stream); tmpFree(valsB, stream); tmpFree(cubTemp, stream);
+  tmpFree(children, stream); tmpFree(ranges, stream); tmpFree(parentInner, stream); tmpFree(parentLeaf, stream); tmpFree(flags, stream); tmpFree(nodeDepth, stream);
+  tmpFree(maxDepthDev, stream); tmpFree(leafBox, stream); tmpFree(nodeBox, stream); tmpFree(nodeCost, stream); tmpFree(collapsed, stream);
   cudaFree(out.nodes); cudaFree(out.triInfo); cudaFree(out.triShade);
   out = BvhResult{};
   return false;
