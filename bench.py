@@ -224,6 +224,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-hbm-record", action="store_true", help="skip the HBM-resident roofline record (instanced_10m sub-run, N=1)")
+    ap.add_argument("--tile", type=int, default=0, help="edge of the sharding tiles in pixels (default 64)")
     ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the 3840x2160 sub-record (BASELINE.json configs[3])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -274,7 +275,7 @@ def main():
     cold_build_ms = float(ctx.stats().ms_build)
     ctx.commit(args.build_mode)            # again, warm: the first build pays CUDA's lazy kernel loading and first allocations
     _, integral, _ = ctx.build_env_accel(scene.env)
-    TILE = 64
+    TILE = args.tile if args.tile > 0 else 64
     shard = (rank, world) if use_dist else (0, 1)
 
     def make_opts(**kw):
@@ -566,7 +567,7 @@ def main():
                                          "what": "vkrt_scene_commit: instance flattening + BVH build, outside the timed region (SURVEY 8d)"},
                            "resolution": [W, H], "max_depth": cfg["depth"], "spp_per_step": 1, "pbr_mode": args.pbr_mode,
                            "frames_in_flight": m["fif"],
-                           "sharding": f"{world} x interleaved 64x64 tiles, gather of owned pixels to rank 0" if use_dist else "none",
+                           "sharding": f"{world} x interleaved {TILE}x{TILE} tiles, gather of owned pixels to rank 0" if use_dist else "none",
                            "l2": "per-step wavefront state (~170 B x %d paths) exceeds the 126 MB L2; the BVH/geometry is L2-resident by design" % (W * H),
                            "rays_counted": "ClosestHit + AnyHit calls (device counters)",
                            "vulkan": vulkan_probe()},

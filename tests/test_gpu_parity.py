@@ -449,7 +449,7 @@ def test_fast_shading_against_precise_and_oracle(vk, ob, gpu, pbr):
 
 
 @pytest.mark.parametrize("env", [{"VKRT_BVH_WIDTH": "4"}, {"VKRT_NODE_FORMAT": "q32"}, {"VKRT_NODE_FORMAT": "lohi"}, {"VKRT_TRACE_VARIANT": "200"},
-                                 {"VKRT_OVERLAP": "0"}])
+                                 {"VKRT_OVERLAP": "0"}, {"VKRT_DUAL_SLOT": "0"}])
 def test_non_default_traversal_kernels_in_subprocess(env):
     """The traversal kernel is chosen once per process (environment): the 4-wide tree, the 16-bit grid nodes, the min/max fp32
     nodes, the if-if loop and the single-stream schedule must give the same bit-exact hits and the same images as the default."""

@@ -102,6 +102,31 @@ struct Wavefront
   uint32_t  numPaths;  // numLocalPixels * framesInFlight
 };
 
+// Wavefront state streams through the GPU once per bounce (gigabytes per launch) while the scene -- BVH, shading records, materials,
+// textures: ~100 MB -- is reused by every ray.  VKRT_STREAM_HINTS marks the state accesses evict-first (ld.global.cs / st.global.cs) so
+// that they do not push the scene out of the 126 MB L2.
+#ifndef VKRT_STREAM_HINTS
+#define VKRT_STREAM_HINTS 1
+#endif
+template <class T>
+VKRT_D T ldS(const T* p)
+{
+#if VKRT_STREAM_HINTS
+  return __ldcs(p);
+#else
+  return *p;
+#endif
+}
+template <class T>
+VKRT_D void stS(T* p, T v)
+{
+#if VKRT_STREAM_HINTS
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+
 struct TraceStats  // device counters
 {
   unsigned long long closestRays, shadowRays, nodesVisited, trisTested, shadowNodes, shadowTris, shadowRaysPrimary;

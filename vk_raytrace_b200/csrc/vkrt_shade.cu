@@ -92,12 +92,12 @@ __global__ void __launch_bounds__(256) raygenKernel(const __grid_constant__ Scen
   float3 aperturePos = (m_cosf(cam_r1) * f3(cam_right) + m_sinf(cam_r1) * f3(cam_up)) * sqrtf(cam_r2);
   float3 rayDir      = normalize(focalPoint - aperturePos);
 
-  wf.rayO[p]     = f4(f3(origin) + aperturePos, kInfinity);
-  wf.rayD[p]     = f4(rayDir, __uint_as_float(seed));
-  wf.thr[p]      = f4(1.f, 1.f, 1.f, __uint_as_float(seed));
-  wf.rad[p]      = f4(0.f, 0.f, 0.f, 0.f);
-  wf.absb[p]     = f4(0.f, 0.f, 0.f, 0.f);
-  wf.queueCur[p] = p;
+  stS(&wf.rayO[p], f4(f3(origin) + aperturePos, kInfinity));
+  stS(&wf.rayD[p], f4(rayDir, __uint_as_float(seed)));
+  stS(&wf.thr[p], f4(1.f, 1.f, 1.f, __uint_as_float(seed)));
+  stS(&wf.rad[p], f4(0.f, 0.f, 0.f, 0.f));
+  stS(&wf.absb[p], f4(0.f, 0.f, 0.f, 0.f));
+  stS(&wf.queueCur[p], p);
 }
 
 #endif  // !VKRT_FAST_MATH
@@ -511,9 +511,9 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(cons
     bool        live = false;
     if(valid)
     {
-      p = wf.queueCur[i];
-      const float4 rd = wf.rayD[p], h = wf.hit[p];
-      const float4 t4 = wf.thr[p], r4 = wf.rad[p], a4 = wf.absb[p];
+      p = ldS(&wf.queueCur[i]);
+      const float4 rd = ldS(&wf.rayD[p]), h = ldS(&wf.hit[p]);
+      const float4 t4 = ldS(&wf.thr[p]), r4 = ldS(&wf.rad[p]), a4 = ldS(&wf.absb[p]);
       b.rayD = f3(rd); b.throughput = f3(t4); b.radiance = f3(r4); b.absorption = f3(a4);
       b.seed = __float_as_uint(t4.w);
       if(sc.hasNonOpaque)
@@ -528,9 +528,9 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(cons
       bouncePhaseSample<PBR>(sc, fp, b, out);
     if(valid)
     {
-      wf.thr[p]  = f4(b.throughput, __uint_as_float(b.seed));
-      wf.rad[p]  = f4(b.radiance, 0.f);
-      wf.absb[p] = f4(b.absorption, 0.f);
+      stS(&wf.thr[p], f4(b.throughput, __uint_as_float(b.seed)));
+      stS(&wf.rad[p], f4(b.radiance, 0.f));
+      stS(&wf.absb[p], f4(b.absorption, 0.f));
     }
     // warp-aggregated queue appends (all 32 lanes reach this point)
     const unsigned mNext = __ballot_sync(0xffffffffu, out.wantNext);
@@ -546,16 +546,16 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(cons
     const unsigned lt = (1u << lane) - 1u;
     if(out.wantNext)
     {
-      wf.queueNext[baseNext + __popc(mNext & lt)] = p;
-      wf.rayO[p] = f4(out.nextO, kInfinity);
-      wf.rayD[p] = f4(out.nextD, __uint_as_float(b.seed));
+      stS(&wf.queueNext[baseNext + __popc(mNext & lt)], p);
+      stS(&wf.rayO[p], f4(out.nextO, kInfinity));
+      stS(&wf.rayD[p], f4(out.nextD, __uint_as_float(b.seed)));
     }
     if(out.wantShadow)
     {
       const uint32_t k = baseSh + __popc(mSh & lt);
-      wf.shO[k] = f4(out.shO, out.shTmax);
-      wf.shD[k] = f4(out.shD, __uint_as_float(out.shSeed));
-      wf.shC[k] = f4(out.shC, __uint_as_float(p));
+      stS(&wf.shO[k], f4(out.shO, out.shTmax));
+      stS(&wf.shD[k], f4(out.shD, __uint_as_float(out.shSeed)));
+      stS(&wf.shC[k], f4(out.shC, __uint_as_float(p)));
     }
     __syncthreads();
   }

@@ -199,8 +199,8 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
         const uint32_t i = base + (uint32_t)__popc(idle & lt);
         if(i < n)
         {
-          slot = (MODE != MODE_SHADOW_RESOLVE && L.queue) ? L.queue[i] : i;
-          const float4 ro = L.rayO[slot], rd = L.rayD[slot];
+          slot = (MODE != MODE_SHADOW_RESOLVE && L.queue) ? ldS(&L.queue[i]) : i;
+          const float4 ro = ldS(&L.rayO[slot]), rd = ldS(&L.rayD[slot]);
           o = f3(ro); d = f3(rd);
           const float tmax = ro.w;
           bestT   = tmax; bestU = 0.f; bestV = 0.f; bestTri = ~0u;
@@ -537,17 +537,17 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
           L.cost[path].w += (float)(nNodes + nTris - rayBase);
         }
         if(MODE == MODE_CLOSEST)
-          L.hit[slot] = (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(bestT, bestU, bestV, __uint_as_float(bestTri));
+          stS(&L.hit[slot], (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(bestT, bestU, bestV, __uint_as_float(bestTri)));
         else if(MODE == MODE_ANY_PROBE)
           L.hit[slot] = (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(0.f, 0.f, 0.f, __uint_as_float(0u));
         else if(bestTri == ~0u)
         {
           // unoccluded: radiance += contribution (one shadow ray per path per bounce: no race)
-          const float4   c    = L.shC[slot];
+          const float4   c    = ldS(&L.shC[slot]);
           const uint32_t path = __float_as_uint(c.w);
-          float4         rad  = L.rad[path];
+          float4         rad  = ldS(&L.rad[path]);
           rad.x += c.x; rad.y += c.y; rad.z += c.z;
-          L.rad[path] = rad;
+          stS(&L.rad[path], rad);
         }
         haveRay = false;
       }
@@ -646,8 +646,8 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_WIDE_MINBLOCKS) traceKernelW
         const uint32_t i = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
         if(i < n)
         {
-          slot = (MODE != MODE_SHADOW_RESOLVE && L.queue) ? L.queue[i] : i;
-          const float4 ro = L.rayO[slot], rd = L.rayD[slot];
+          slot = (MODE != MODE_SHADOW_RESOLVE && L.queue) ? ldS(&L.queue[i]) : i;
+          const float4 ro = ldS(&L.rayO[slot]), rd = ldS(&L.rayD[slot]);
           o = f3(ro); d = f3(rd);
           const float tmax = ro.w;
           bestT   = tmax; bestU = 0.f; bestV = 0.f; bestTri = ~0u;
@@ -829,16 +829,16 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_WIDE_MINBLOCKS) traceKernelW
           L.cost[path].w += (float)(nNodes + nTris - rayBase);
         }
         if(MODE == MODE_CLOSEST)
-          L.hit[slot] = (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(bestT, bestU, bestV, __uint_as_float(bestTri));
+          stS(&L.hit[slot], (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(bestT, bestU, bestV, __uint_as_float(bestTri)));
         else if(MODE == MODE_ANY_PROBE)
           L.hit[slot] = (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(0.f, 0.f, 0.f, __uint_as_float(0u));
         else if(bestTri == ~0u)
         {
-          const float4   c    = L.shC[slot];
+          const float4   c    = ldS(&L.shC[slot]);
           const uint32_t path = __float_as_uint(c.w);
-          float4         rad  = L.rad[path];
+          float4         rad  = ldS(&L.rad[path]);
           rad.x += c.x; rad.y += c.y; rad.z += c.z;
-          L.rad[path] = rad;
+          stS(&L.rad[path], rad);
         }
         haveRay = false;
       }
