@@ -224,6 +224,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-hbm-record", action="store_true", help="skip the HBM-resident roofline record (instanced_10m sub-run, N=1)")
+    ap.add_argument("--scene-file", default=None, help="render a glTF 2.0 file (.gltf / .glb: the real Sponza / DamagedHelmet when present) through the "
+                    "C++ ingest (libvkrt_host.so) instead of a procedural workload; resolution / depth from --width --height --depth")
+    ap.add_argument("--env-file", default=None, help="Radiance .hdr or .pfm environment for --scene-file (default: the procedural sky)")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--depth", type=int, default=8)
     ap.add_argument("--tile", type=int, default=0, help="edge of the sharding tiles in pixels (default 64)")
     ap.add_argument("--no-c4", action="store_true", help="N > 1: skip the 3840x2160 sub-record (BASELINE.json configs[3])")
     args = ap.parse_args()
@@ -233,6 +239,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cfg = WORKLOADS[args.workload]
+    if args.scene_file:
+        cfg = dict(scene="file", w=args.width, h=args.height, depth=args.depth)
+        args.workload = "file:" + os.path.basename(args.scene_file)
+        args.no_cpu_baseline = True      # the CPU oracle has no glTF ingest of its own: it is fed from in-memory scenes only
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the CPU oracle has no glTF file ingest; --scene-file runs are GPU-arm only"}))
+            return
     W, H = cfg["w"], cfg["h"]
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -267,14 +281,34 @@ def main():
     torch.cuda.set_device(device)
     dev = f"cuda:{device}"
 
-    scene = make_scene(cfg)
-    if args.build_mode < 0:
-        args.build_mode = default_build_mode(scene.num_triangles())
     ctx = Context(device)
-    upload_scene(ctx, scene, W, H, build_mode=args.build_mode)
-    cold_build_ms = float(ctx.stats().ms_build)
-    ctx.commit(args.build_mode)            # again, warm: the first build pays CUDA's lazy kernel loading and first allocations
-    _, integral, _ = ctx.build_env_accel(scene.env)
+    if args.scene_file:
+        # Scene::load through the C++ ingest (vk_raytrace_b200/host: glTF + PNG / JPEG), environment from a file or the procedural sky
+        from types import SimpleNamespace
+        from vk_raytrace_b200 import scenes as _scenes
+        if args.build_mode < 0:
+            args.build_mode = default_build_mode(0)
+        info = ctx.load_gltf(args.scene_file, args.build_mode)
+        cold_build_ms = float(ctx.stats().ms_build)
+        if args.env_file:
+            integral, _, _ = ctx.load_environment(args.env_file)
+        else:
+            env = _scenes.sky_environment(1024, 512, 100)
+            _, integral, _ = ctx.build_env_accel(env)
+            ctx.set_environment(env)
+        scene = SimpleNamespace(name=args.workload, env=None, lights=[None] * int(info.lights),
+                                camera=dict(eye=tuple(info.eye), center=tuple(info.center), up=tuple(info.up), fov=float(info.yfov_degrees)),
+                                num_triangles=lambda: int(info.triangles))
+        ctx.set_camera(ctx.make_camera(scene.camera["eye"], scene.camera["center"], scene.camera["up"], scene.camera["fov"], W / H, 0.0, int(info.lights)))
+        ctx.output_create(W, H)
+    else:
+        scene = make_scene(cfg)
+        if args.build_mode < 0:
+            args.build_mode = default_build_mode(scene.num_triangles())
+        upload_scene(ctx, scene, W, H, build_mode=args.build_mode)
+        cold_build_ms = float(ctx.stats().ms_build)
+        ctx.commit(args.build_mode)            # again, warm: the first build pays CUDA's lazy kernel loading and first allocations
+        _, integral, _ = ctx.build_env_accel(scene.env)
     TILE = args.tile if args.tile > 0 else 64
     shard = (rank, world) if use_dist else (0, 1)
 
@@ -446,47 +480,6 @@ def main():
                                "latency of dependent node fetches and by SIMT divergence of incoherent rays.  `algorithmic_gbs` is SURVEY 8d's "
                                "bytes / summed CUDA-event time, reported for continuity, not as a fraction of any peak."}
 
-    # ---- HBM-resident roofline record (the one `frac` is defined for): the 10.4 M-triangle scene, 1.2 GB of nodes + triangles,
-    #      measured in this same run for the 4-wide tree (the default above 1.5 M triangles) and the binary tree
-    roofline = None
-    if not use_dist and not args.no_hbm_record:
-        def hbm_record(width_flag, label):
-            c2 = ctx if args.workload == "instanced_10m" and width_flag == 0 else Context(device)
-            cfg2 = WORKLOADS["instanced_10m"]
-            if c2 is not ctx:
-                sc2 = make_scene(cfg2)
-                upload_scene(c2, sc2, cfg2["w"], cfg2["h"], build_mode=default_build_mode(sc2.num_triangles()) | width_flag)
-            st2 = S.default_rtx_state(cfg2["w"], cfg2["h"], maxDepth=cfg2["depth"], fireflyClampThreshold=4.0)
-            k = 8
-            o2 = make_opts(frames_in_flight=k)
-            c2.render(st2, k, o2)                         # warm-up
-            p2, n2 = kernel_profile(c2, st2, k, k, o2)
-            rec = trace_record(p2, n2)
-            tri = int(c2.stats().num_triangles)
-            nodes = int(c2.stats().num_bvh_nodes)
-            if c2 is not ctx:
-                c2.close()
-            rec.update({"tree": label, "triangles": tri, "bvh_bytes": nodes * 64 + tri * 48, "frames": k})
-            return rec
-        r4 = hbm_record(0x200, "bvh4")
-        r2 = hbm_record(0x100, "bvh2")
-        traffic = profile_traffic("instanced_10m_closest_dram_bytes_per_launch")
-        roofline = {"kernel": "traceKernelWide<CLOSEST>", "workload": "instanced_10m (HBM resident: %.2f GB of nodes + triangles)" % (r4["bvh_bytes"] / 1e9),
-                    "bound": "hbm", "achieved": r4["achieved"], "peak": peak, "unit": "GB/s", "frac": r4["achieved"] / peak,
-                    "traffic": traffic, "peak_source": peak_src, "per_ray": r4["per_ray"], "ms_trace_closest": r4["ms_trace_closest"],
-                    "closest_rays": r4["closest_rays"], "frames": r4["frames"],
-                    "bvh2": {"achieved": r2["achieved"], "frac": r2["achieved"] / peak, "per_ray": r2["per_ray"], "ms_trace_closest": r2["ms_trace_closest"]},
-                    "headline_kernel": headline_kernel,
-                    "note": "achieved = algorithmic bytes (ray 32 + hit 16 + 64 per node visited + 48 per triangle tested, visit counters of an "
-                            "instrumented pass over the same frames) / summed CUDA-event time of the closest-hit launches of those frames; both "
-                            "trees fetch 64-byte nodes.  `traffic` = ncu dram bytes of one closest-hit launch (profiles/).  The headline workload's "
-                            "BVH is L2 resident: see headline_kernel."}
-    else:
-        roofline = {"kernel": headline_kernel["kernel"], "workload": args.workload, "bound": headline_kernel["bound"], "achieved": head["achieved"],
-                    "peak": peak, "unit": "GB/s", "frac": (head["achieved"] / peak) if not l2_resident else None, "traffic": None,
-                    "peak_source": peak_src, "per_ray": head["per_ray"], "headline_kernel": headline_kernel,
-                    "note": "multi-GPU / --no-hbm-record run: the HBM-resident record is measured by the N=1 default run"}
-
     # ---- e2e: the same metric through the C ABI as an interactive host drives it, one definition for every N: per step a host
     #      SceneCamera goes in, ONE frame is rendered (sharded when N > 1, then exchanged), and the tonemapped RGBA8 frame comes
     #      back to page-locked host memory on rank 0.  The read-back of frame f overlaps the rendering of frame f+1
@@ -542,6 +535,47 @@ def main():
         if rank == 0:
             for b in bufs:
                 ctx.host_free(b)
+
+    # ---- HBM-resident roofline record (the one `frac` is defined for): the 10.4 M-triangle scene, 1.2 GB of nodes + triangles,
+    #      measured in this same run for the 4-wide tree (the default above 1.5 M triangles) and the binary tree
+    roofline = None
+    if not use_dist and not args.no_hbm_record:
+        def hbm_record(width_flag, label):
+            c2 = ctx if args.workload == "instanced_10m" and width_flag == 0 else Context(device)
+            cfg2 = WORKLOADS["instanced_10m"]
+            if c2 is not ctx:
+                sc2 = make_scene(cfg2)
+                upload_scene(c2, sc2, cfg2["w"], cfg2["h"], build_mode=default_build_mode(sc2.num_triangles()) | width_flag)
+            st2 = S.default_rtx_state(cfg2["w"], cfg2["h"], maxDepth=cfg2["depth"], fireflyClampThreshold=4.0)
+            k = 8
+            o2 = make_opts(frames_in_flight=k)
+            c2.render(st2, k, o2)                         # warm-up
+            p2, n2 = kernel_profile(c2, st2, k, k, o2)
+            rec = trace_record(p2, n2)
+            tri = int(c2.stats().num_triangles)
+            nodes = int(c2.stats().num_bvh_nodes)
+            if c2 is not ctx:
+                c2.close()
+            rec.update({"tree": label, "triangles": tri, "bvh_bytes": nodes * 64 + tri * 48, "frames": k})
+            return rec
+        r4 = hbm_record(0x200, "bvh4")
+        r2 = hbm_record(0x100, "bvh2")
+        traffic = profile_traffic("instanced_10m_closest_dram_bytes_per_launch")
+        roofline = {"kernel": "traceKernelWide<CLOSEST>", "workload": "instanced_10m (HBM resident: %.2f GB of nodes + triangles)" % (r4["bvh_bytes"] / 1e9),
+                    "bound": "hbm", "achieved": r4["achieved"], "peak": peak, "unit": "GB/s", "frac": r4["achieved"] / peak,
+                    "traffic": traffic, "peak_source": peak_src, "per_ray": r4["per_ray"], "ms_trace_closest": r4["ms_trace_closest"],
+                    "closest_rays": r4["closest_rays"], "frames": r4["frames"],
+                    "bvh2": {"achieved": r2["achieved"], "frac": r2["achieved"] / peak, "per_ray": r2["per_ray"], "ms_trace_closest": r2["ms_trace_closest"]},
+                    "headline_kernel": headline_kernel,
+                    "note": "achieved = algorithmic bytes (ray 32 + hit 16 + 64 per node visited + 48 per triangle tested, visit counters of an "
+                            "instrumented pass over the same frames) / summed CUDA-event time of the closest-hit launches of those frames; both "
+                            "trees fetch 64-byte nodes.  `traffic` = ncu dram bytes of one closest-hit launch (profiles/).  The headline workload's "
+                            "BVH is L2 resident: see headline_kernel."}
+    else:
+        roofline = {"kernel": headline_kernel["kernel"], "workload": args.workload, "bound": headline_kernel["bound"], "achieved": head["achieved"],
+                    "peak": peak, "unit": "GB/s", "frac": (head["achieved"] / peak) if not l2_resident else None, "traffic": None,
+                    "peak_source": peak_src, "per_ray": head["per_ray"], "headline_kernel": headline_kernel,
+                    "note": "multi-GPU / --no-hbm-record run: the HBM-resident record is measured by the N=1 default run"}
 
     # ---- C4 of BASELINE.json: the same scene at 3840x2160, tile-sharded over the ranks, in the same run (N > 1)
     c4 = None

@@ -61,9 +61,9 @@ typedef struct vkrt_render_opts
   int32_t shard_rank;       /* this context renders tiles t with t % shard_count == shard_rank */
   int32_t shard_count;      /* 0 or 1 = whole image                                    */
   int32_t count_traversal;  /* 1 = run the instrumented traversal kernels (visit counters) */
-  int32_t sort_rays;        /* 1 = order each bounce's compacted ray queue by direction octant + origin Morton key before
-                               tracing it (same image; one host synchronisation per bounce).  Default 0: measured slower
-                               or equal on the bench scenes, see profiles/README.md */
+  int32_t sort_rays;        /* 1 = order each bounce's compacted ray queue by direction octant + origin Morton bucket before tracing it
+                               (hand-written device-side bucket sort, no host synchronisation; same image).  Default 0: measured
+                               neutral to slightly slower on the bench scenes, see profiles/README.md */
   int32_t profile;          /* 1 = time every kernel family with CUDA events (vkrt_stats.ms_*) */
   int32_t precise_shading;  /* 0 (default): the shade kernel uses approximate division / sqrt and SFU sin/cos/exp/log/pow, as a GLSL
                                compiler does; 1: IEEE-exact arithmetic throughout (what the oracle comparisons at 1e-4 use).

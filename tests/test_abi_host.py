@@ -170,3 +170,18 @@ def test_adaptor_compiles_against_reference_header(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-3000:]
     assert subprocess.run([exe]).returncode == 0
+
+
+def test_host_library_loads_and_exports(vk):
+    """libvkrt_host.so (include/vkrt_host.h): every declared symbol is exported; a bad path is an error with a message, no GPU needed."""
+    from vk_raytrace_b200 import lib as L
+    hdr = open(os.path.join(ROOT, "include", "vkrt_host.h")).read()
+    declared = sorted(set(re.findall(r"\b(vkrt_host_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(L.HOST_EXPORTS)
+    host = L.load_host_library()
+    for name in declared:
+        assert hasattr(host, name)
+    info = L.HostSceneInfo()
+    assert C.sizeof(info) == 96
+    rc = host.vkrt_host_load_gltf(None, b"/nonexistent.gltf", 0, C.byref(info))
+    assert rc != 0 and b"null" in host.vkrt_host_last_error()

@@ -704,3 +704,32 @@ def test_forced_tree_width_gives_identical_hits(vk, ob, gpu):
     o = ob.Oracle()
     vk.upload_scene(o, sc, 16, 16)
     assert np.array_equal(hits[0], o.trace_rays(rays, True).view(np.uint32))
+
+
+def test_scene_file_through_host_library_and_bench(vk, gpu, tmp_path):
+    """`bench.py --scene-file` / vkrt_host_load_gltf: a glTF file fed through libvkrt_host.so gives the geometry of the in-memory
+    upload (same hit distances and barycentrics for 20 k rays; triangle numbering follows the importer's mesh order), and the bench
+    prints a valid line for it."""
+    import json
+    import subprocess
+    import sys
+    from vk_raytrace_b200.gltf_export import export_gltf
+    sc = small_sponza()
+    gltf, env = export_gltf(sc, str(tmp_path), "s")
+    rays = random_rays(20000, 5, 14.0, centre=(0, 3, 0))
+    vk.upload_scene(gpu, sc, 32, 32, build_mode=4)
+    want = gpu.trace_rays(rays, True)
+    n_tri = gpu.stats().num_triangles
+    info = gpu.load_gltf(gltf, 4)
+    integral, ew, eh = gpu.load_environment(env)
+    assert info.triangles == n_tri == gpu.stats().num_triangles and info.lights == len(sc.lights) and info.camera_from_file == 1
+    assert (ew, eh) == (sc.env.shape[1], sc.env.shape[0]) and integral > 0
+    got = gpu.trace_rays(rays, True)
+    assert np.array_equal(got[:, :3].view(np.uint32), want[:, :3].view(np.uint32))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--scene-file", gltf, "--env-file", env, "--width", "320", "--height", "200", "--steps", "4",
+                          "--warmup", "3", "--no-hbm-record"], capture_output=True, text=True, cwd=root, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["config"]["workload"].startswith("file:") and line["value"] > 0 and line["e2e"]["value"] > 0
+    assert line["config"]["triangles"] == n_tri and line["rays"] >= 4 * 320 * 200

@@ -2,6 +2,7 @@
 drive; `SceneDesc` is the backend-neutral scene description that both the CUDA library
 and the CPU oracle (tests only) are fed from, through the same call sequence."""
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional
 
@@ -179,6 +180,27 @@ class Context:
 
     def set_camera(self, cam):
         self._ck(self.lib.vkrt_set_camera(self.h, C.byref(cam)), "set_camera")
+
+    # ---- files (libvkrt_host.so, include/vkrt_host.h) ----
+    def load_gltf(self, path, build_mode=0):
+        """Scene::load from a .gltf / .glb file through the C++ ingest; returns lib.HostSceneInfo (camera, counts, bounds)."""
+        from .lib import HostSceneInfo, load_host_library
+        host = load_host_library()
+        info = HostSceneInfo()
+        rc = host.vkrt_host_load_gltf(self.h, os.fsencode(path), build_mode, C.byref(info))
+        if rc != 0:
+            raise RuntimeError(f"load_gltf: error {rc}: {host.vkrt_host_last_error().decode()}")
+        return info
+
+    def load_environment(self, path):
+        """HdrSampling::loadEnvironment from a Radiance .hdr / .pfm file; returns (integral, width, height)."""
+        from .lib import load_host_library
+        host = load_host_library()
+        integ, w, h = C.c_float(), C.c_uint32(), C.c_uint32()
+        rc = host.vkrt_host_load_environment(self.h, os.fsencode(path), C.byref(integ), C.byref(w), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"load_environment: error {rc}: {host.vkrt_host_last_error().decode()}")
+        return integ.value, w.value, h.value
 
     # ---- output ----
     def output_create(self, width, height, device_ptr=None):

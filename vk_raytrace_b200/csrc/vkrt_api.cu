@@ -50,6 +50,10 @@ struct WfSlot
   size_t       capacity = 0;  // paths
   cudaStream_t s = nullptr, s2 = nullptr;
   cudaEvent_t  evShade = nullptr, evShadow = nullptr, evJoin = nullptr, evJoin2 = nullptr;
+  // ray sort (opts.sort_rays): third queue buffer (rotates with queueCur / queueNext) + keys and histogram, sized like the slot
+  uint32_t* sortQueue = nullptr;
+  void*     sortScratch = nullptr;
+  size_t    sortCapacity = 0;
 };
 
 struct vkrt_ctx
@@ -82,10 +86,6 @@ struct vkrt_ctx
   Light*               dLights = nullptr;
   TexDesc*             dTexDescs = nullptr;
   AlphaMat*            dAlphaMats = nullptr;
-  // ray sort (opts.sort_rays): allocated on first use, sized like the wavefront
-  uint32_t *sortKeysA = nullptr, *sortKeysB = nullptr, *sortQueueAlt = nullptr;
-  void*     sortTemp = nullptr;
-  size_t    sortTempSize = 0, sortCapacity = 0;
   std::vector<uchar4*> dTexData;
   float4*              dEnv = nullptr;
   EnvAccel*            dEnvAccel = nullptr;
@@ -210,6 +210,8 @@ static void freeScene(vkrt_ctx* c)
   c->dMat = nullptr; c->dLights = nullptr; c->dTexDescs = nullptr; c->dAlphaMats = nullptr;
   c->bvh = BvhResult{};
   c->hostTriInfo.clear();
+  if(c->committed)
+    cudaCtxResetPersistingL2Cache();  // the BVH arena's persisting lines (device-wide set-aside) must not outlive the scene
   c->committed = false;
 }
 
@@ -218,33 +220,16 @@ static void freeSlot(WfSlot& sl)
   Wavefront& w = sl.wf;
   cudaFree(w.rayO); cudaFree(w.rayD); cudaFree(w.hit); cudaFree(w.thr); cudaFree(w.rad); cudaFree(w.absb); cudaFree(w.sum);
   cudaFree(w.shO); cudaFree(w.shD); cudaFree(w.shC); cudaFree(w.queueCur); cudaFree(w.queueNext); cudaFree(w.counters);
-  w           = Wavefront{};
-  sl.capacity = 0;
+  cudaFree(sl.sortQueue); cudaFree(sl.sortScratch);
+  sl.sortQueue    = nullptr;
+  sl.sortScratch  = nullptr;
+  sl.sortCapacity = 0;
+  w               = Wavefront{};
+  sl.capacity     = 0;
 }
 static void freeWavefront(vkrt_ctx* c)
 {
   for(auto& sl : c->slots) freeSlot(sl);
-  cudaFree(c->sortKeysA); cudaFree(c->sortKeysB); cudaFree(c->sortQueueAlt); cudaFree(c->sortTemp);
-  c->sortKeysA = c->sortKeysB = c->sortQueueAlt = nullptr;
-  c->sortTemp = nullptr;
-  c->sortTempSize = c->sortCapacity = 0;
-}
-
-// buffers of the optional ray sort, sized like the wavefront (grow-only)
-static int ensureSortBuffers(vkrt_ctx* ctx, size_t paths)
-{
-  if(paths <= ctx->sortCapacity)
-    return VKRT_OK;
-  cudaFree(ctx->sortKeysA); cudaFree(ctx->sortKeysB); cudaFree(ctx->sortQueueAlt); cudaFree(ctx->sortTemp);
-  ctx->sortKeysA = ctx->sortKeysB = ctx->sortQueueAlt = nullptr;
-  ctx->sortTemp = nullptr;
-  ctx->sortCapacity = 0;
-  CTX_CHECK(cudaMalloc(&ctx->sortKeysA, 4 * paths)); CTX_CHECK(cudaMalloc(&ctx->sortKeysB, 4 * paths));
-  CTX_CHECK(cudaMalloc(&ctx->sortQueueAlt, 4 * paths));
-  ctx->sortTempSize = sortTempBytes((uint32_t)paths);
-  CTX_CHECK(cudaMalloc(&ctx->sortTemp, ctx->sortTempSize ? ctx->sortTempSize : 16));
-  ctx->sortCapacity = paths;
-  return VKRT_OK;
 }
 
 static cudaEvent_t getEvent(vkrt_ctx* c)
@@ -1031,6 +1016,19 @@ int vkrt_output_unpack_shard(vkrt_ctx* ctx, int32_t tile_size, int32_t shard_ran
 }
 
 // ---- render --------------------------------------------------------------------------------------------
+static int ensureSlotSort(vkrt_ctx* ctx, WfSlot& sl)
+{
+  if(sl.sortCapacity >= sl.capacity)
+    return VKRT_OK;
+  CTX_CHECK(syncAll(ctx));
+  cudaFree(sl.sortQueue); cudaFree(sl.sortScratch);
+  sl.sortQueue = nullptr; sl.sortScratch = nullptr; sl.sortCapacity = 0;
+  CTX_CHECK(cudaMalloc(&sl.sortQueue, 4 * sl.capacity));
+  CTX_CHECK(cudaMalloc(&sl.sortScratch, sortScratchBytes((uint32_t)sl.capacity)));
+  sl.sortCapacity = sl.capacity;
+  return VKRT_OK;
+}
+
 static int ensureSlot(vkrt_ctx* ctx, WfSlot& sl, size_t paths)
 {
   if(paths <= sl.capacity)
@@ -1085,7 +1083,7 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
   static const bool overlapEnv = []() { const char* e = getenv("VKRT_OVERLAP"); return !e || atoi(e) != 0; }();
   static const bool dualEnv    = []() { const char* e = getenv("VKRT_DUAL_SLOT"); return !e || atoi(e) != 0; }();
   const bool overlap  = overlapEnv && !timing && !heatmap;
-  const bool dual     = overlap && dualEnv && !o.sort_rays;
+  const bool dual     = overlap && dualEnv;
   // VKRT_SHADING=precise forces the IEEE-exact shade kernel for callers that cannot pass options (the C++ tools in tests)
   static const bool envPrecise = []() { const char* e = getenv("VKRT_SHADING"); return e && !strcmp(e, "precise"); }();
   if(envPrecise) o.precise_shading = 1;
@@ -1121,7 +1119,7 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
     size_t freeB = 0, totalB = 0;
     if((size_t)nLocal * perBatch * slotsNow > have && cudaMemGetInfo(&freeB, &totalB) == cudaSuccess)
     {
-      const size_t perPath = 10 * sizeof(float4) + 8 + (o.sort_rays ? 12 : 0);
+      const size_t perPath = 10 * sizeof(float4) + 8 + (o.sort_rays ? 8 : 0);
       const size_t fit     = (freeB / 2 + have * perPath) / (perPath * (size_t)nLocal * slotsNow);
       perBatch             = (int)std::max<size_t>(1, std::min<size_t>((size_t)perBatch, fit));
     }
@@ -1134,8 +1132,6 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
   if(slotsNow == 2 || !autoFif)
     for(int k = 0; k < (dual ? 2 : 1) && rc == VKRT_OK; k++)
       rc = ensureSlot(ctx, ctx->slots[k], (size_t)nLocal * reserve);
-  if(rc == VKRT_OK && o.sort_rays)
-    rc = ensureSortBuffers(ctx, (size_t)nLocal * reserve);
   if(rc != VKRT_OK) return rc;
   perBatch = std::min(perBatch, num_frames);
 
@@ -1146,20 +1142,22 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
     const int batch = std::min(perBatch, num_frames - done);
     WfSlot&   sl    = ctx->slots[dual ? (ctx->nextSlot++ & 1u) : 0u];
     rc = ensureSlot(ctx, sl, (size_t)nLocal * perBatch);  // no-op once the slot is large enough
+    if(rc == VKRT_OK && o.sort_rays)
+      rc = ensureSlotSort(ctx, sl);
     if(rc != VKRT_OK) return rc;
     cudaStream_t st = timing ? ctx->stream : sl.s;  // ScopedTimer records on ctx->stream (== slots[0].s; timing is single slot)
     Wavefront wf      = sl.wf;
     wf.numPaths       = nLocal * (uint32_t)batch;
     wf.numLocalPixels = nLocal;
     wf.pixelOfLocal   = dPix;
-    uint32_t* sortAlt = ctx->sortQueueAlt;  // third queue buffer of the optional ray sort (rotates with queueCur)
+    uint32_t* sortAlt = sl.sortQueue;  // third queue buffer of the optional ray sort (rotates with queueCur)
     // Bounce from which the fused tail kernel takes over (vkrt_render_opts.tail_from, else VKRT_TAIL_FROM: 0 never, n > 0 from bounce n; default: from bounce 3
     // for small wavefronts -- an interactive frame, a thin multi-GPU shard -- where launch gaps and kernel tails outweigh the
     // less efficient one-thread-per-path traversal; large batches keep one launch per stage).  Same image either way.
     static const int tailEnv = []() { const char* e = getenv("VKRT_TAIL_FROM"); return e ? atoi(e) : -1; }();
     static const long long tailAutoPaths = []() { const char* e = getenv("VKRT_TAIL_AUTO_PATHS"); return e ? atoll(e) : (long long)(9u << 20); }();
     int tailFrom = 1 << 30;
-    if(!counting && !heatmap && !o.sort_rays)
+    if(!counting && !heatmap)
     {
       const int want = o.tail_from != 0 ? o.tail_from : (tailEnv == 0 ? -1 : (tailEnv > 0 ? tailEnv : 0));  // options, then environment
       if(want > 0)
@@ -1200,19 +1198,12 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
         }
         if(o.sort_rays && depth >= 1)
         {
-          // order this bounce's queue by (direction octant, origin Morton code); the live count is read back (one host
-          // synchronisation per bounce, only in this mode).  Primary rays are coherent already.
-          uint32_t live = 0;
-          CTX_CHECK(cudaMemcpyAsync(&live, wf.counters, 4, cudaMemcpyDeviceToHost, st));
-          CTX_CHECK(cudaStreamSynchronize(st));
-          if(live > 64)
-          {
-            ScopedTimer t(ctx, timing, T_SORT);
-            if(launchSortQueue(st, ctx->view, wf.rayO, wf.rayD, wf.queueCur, sortAlt, live, ctx->sortKeysA, ctx->sortKeysB, ctx->sortTemp,
-                               ctx->sortTempSize))
-              std::swap(wf.queueCur, sortAlt);
-            ctx->stats.kernel_launches += 1 + 4;  // key kernel + the radix-sort passes of the library
-          }
+          // order this bounce's queue by (direction octant, origin Morton bucket): three small kernels that read the live count
+          // from the wavefront counters -- no host synchronisation.  Primary rays are coherent already.
+          ScopedTimer t(ctx, timing, T_SORT);
+          launchSortQueue(st, ctx->view, wf.rayO, wf.rayD, wf.queueCur, sortAlt, wf.counters + 0, (uint32_t)sl.capacity, sl.sortScratch, ctx->numSMs);
+          std::swap(wf.queueCur, sortAlt);
+          ctx->stats.kernel_launches += 3;
         }
         TraceLaunch L{};
         L.rayO = wf.rayO; L.rayD = wf.rayD; L.queue = wf.queueCur; L.count = wf.counters + 0; L.cursor = wf.counters + 3;

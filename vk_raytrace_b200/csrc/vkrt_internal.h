@@ -41,10 +41,10 @@ bool quantizeBvh(cudaStream_t stream, BvhResult& bvh, std::string& err, uint64_t
 // binary tree -> 4-wide nodes on the same grid (call after quantizeBvh)
 bool collapseBvhWide(cudaStream_t stream, BvhResult& bvh, std::string& err, uint64_t* launches);
 
-// vkrt_sort.cu: optional ordering of the ray queue between bounces (octant + origin Morton key)
-size_t sortTempBytes(uint32_t maxItems);
-int    launchSortQueue(cudaStream_t s, const SceneView& scene, const float4* rayO, const float4* rayD, uint32_t* queue, uint32_t* queueAlt,
-                       uint32_t count, uint32_t* keysA, uint32_t* keysB, void* temp, size_t tempBytes);
+// vkrt_sort.cu: optional ordering of the ray queue between bounces (octant + origin Morton buckets), hand written, device side only
+size_t sortScratchBytes(uint32_t maxItems);
+void   launchSortQueue(cudaStream_t s, const SceneView& scene, const float4* rayO, const float4* rayD, const uint32_t* queue, uint32_t* queueOut,
+                       const uint32_t* count, uint32_t capacity, void* scratch, int numSMs);
 
 // vkrt_trace.cu
 struct TraceLaunch

@@ -84,3 +84,31 @@ def load_library():
     lib.vkrt_output_unpack_shard.argtypes = [vp, i32, i32, i32, vp]
     _LIB = lib
     return lib
+
+
+# ---- libvkrt_host.so (include/vkrt_host.h): file ingest in front of the C ABI ----------------------------------------------
+_HOST = None
+HOST_EXPORTS = ["vkrt_host_load_gltf", "vkrt_host_load_environment", "vkrt_host_last_error"]
+
+
+class HostSceneInfo(C.Structure):
+    _fields_ = [("eye", C.c_float * 3), ("center", C.c_float * 3), ("up", C.c_float * 3), ("yfov_degrees", C.c_float), ("camera_from_file", C.c_int32),
+                ("prim_meshes", C.c_uint32), ("nodes", C.c_uint32), ("materials", C.c_uint32), ("textures", C.c_uint32), ("lights", C.c_uint32),
+                ("triangles", C.c_uint64), ("bounds_min", C.c_float * 3), ("bounds_max", C.c_float * 3)]
+
+
+def load_host_library():
+    """libvkrt_host.so next to libvkrt_b200.so (built by __graft_entry__.build()); loads the renderer library first so both share it."""
+    global _HOST
+    if _HOST is not None:
+        return _HOST
+    load_library()
+    path = os.path.join(_HERE, "libvkrt_host.so")
+    if not os.path.exists(path):
+        raise LibraryMissing(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(path)
+    lib.vkrt_host_load_gltf.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.POINTER(HostSceneInfo)]
+    lib.vkrt_host_load_environment.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.vkrt_host_last_error.restype = C.c_char_p
+    _HOST = lib
+    return lib
