@@ -54,6 +54,7 @@ struct WfSlot
   uint32_t* sortQueue = nullptr;
   void*     sortScratch = nullptr;
   size_t    sortCapacity = 0;
+  uint32_t  counterLevels = 0;  // bounces the counter array holds
 };
 
 struct vkrt_ctx
@@ -223,9 +224,10 @@ static void freeSlot(WfSlot& sl)
   cudaFree(sl.sortQueue); cudaFree(sl.sortScratch);
   sl.sortQueue    = nullptr;
   sl.sortScratch  = nullptr;
-  sl.sortCapacity = 0;
-  w               = Wavefront{};
-  sl.capacity     = 0;
+  sl.sortCapacity  = 0;
+  sl.counterLevels = 0;
+  w                = Wavefront{};
+  sl.capacity      = 0;
 }
 static void freeWavefront(vkrt_ctx* c)
 {
@@ -1016,6 +1018,20 @@ int vkrt_output_unpack_shard(vkrt_ctx* ctx, int32_t tile_size, int32_t shard_ran
 }
 
 // ---- render --------------------------------------------------------------------------------------------
+static int ensureCounters(vkrt_ctx* ctx, WfSlot& sl, uint32_t levels)
+{
+  if(levels <= sl.counterLevels && sl.wf.counters)
+    return VKRT_OK;
+  CTX_CHECK(syncAll(ctx));
+  cudaFree(sl.wf.counters);
+  sl.wf.counters = nullptr;
+  levels         = std::max<uint32_t>(levels, 16u);
+  CTX_CHECK(cudaMalloc(&sl.wf.counters, 16ull * levels));
+  CTX_CHECK(cudaMemsetAsync(sl.wf.counters, 0, 16ull * levels, sl.s));
+  sl.counterLevels = levels;
+  return VKRT_OK;
+}
+
 static int ensureSlotSort(vkrt_ctx* ctx, WfSlot& sl)
 {
   if(sl.sortCapacity >= sl.capacity)
@@ -1042,8 +1058,8 @@ static int ensureSlot(vkrt_ctx* ctx, WfSlot& sl, size_t paths)
   CTX_CHECK(cudaMalloc(&w.sum, b)); CTX_CHECK(cudaMalloc(&w.shO, b)); CTX_CHECK(cudaMalloc(&w.shD, b));
   CTX_CHECK(cudaMalloc(&w.shC, b));
   CTX_CHECK(cudaMalloc(&w.queueCur, 4 * paths)); CTX_CHECK(cudaMalloc(&w.queueNext, 4 * paths));
-  CTX_CHECK(cudaMalloc(&w.counters, 64));
-  CTX_CHECK(cudaMemsetAsync(w.counters, 0, 64, sl.s));
+  w.counters = nullptr;  // sized by ensureCounters (depends on maxDepth)
+  sl.counterLevels = 0;
   sl.capacity = paths;
   return VKRT_OK;
 }
@@ -1144,12 +1160,16 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
     rc = ensureSlot(ctx, sl, (size_t)nLocal * perBatch);  // no-op once the slot is large enough
     if(rc == VKRT_OK && o.sort_rays)
       rc = ensureSlotSort(ctx, sl);
+    if(rc == VKRT_OK)
+      rc = ensureCounters(ctx, sl, (uint32_t)state->maxDepth + 2u);
     if(rc != VKRT_OK) return rc;
     cudaStream_t st = timing ? ctx->stream : sl.s;  // ScopedTimer records on ctx->stream (== slots[0].s; timing is single slot)
     Wavefront wf      = sl.wf;
     wf.numPaths       = nLocal * (uint32_t)batch;
     wf.numLocalPixels = nLocal;
     wf.pixelOfLocal   = dPix;
+    wf.clevels        = (uint32_t)state->maxDepth + 2u;
+    wf.cbase          = 0;
     uint32_t* sortAlt = sl.sortQueue;  // third queue buffer of the optional ray sort (rotates with queueCur)
     // Bounce from which the fused tail kernel takes over (vkrt_render_opts.tail_from, else VKRT_TAIL_FROM: 0 never, n > 0 from bounce n; default: from bounce 3
     // for small wavefronts -- an interactive frame, a thin multi-GPU shard -- where launch gaps and kernel tails outweigh the
@@ -1165,6 +1185,7 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
       else if(want == 0 && (long long)wf.numPaths <= tailAutoPaths)
         tailFrom = 3;
     }
+    const bool  fuseFinish = state->maxSamples == 1 && !heatmap;  // one sample per frame: the accumulate kernel applies the firefly clamp itself
     FrameParams fp{};
     fp.state         = *state;
     fp.state.frame   = state->frame + done;
@@ -1181,8 +1202,8 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
       ctx->stats.kernel_launches++;
       for(int depth = 0; depth < state->maxDepth; depth++)
       {
-        fp.depth      = depth;
-        wf.shadowSlot = (uint32_t)(depth & 1);
+        fp.depth = depth;
+        wf.cbase = 4u * (uint32_t)depth;
         if(depth >= tailFrom)
         {
           // fused tail: every remaining bounce of the few paths still alive in one launch (tailKernel, vkrt_shade.cu)
@@ -1201,12 +1222,12 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
           // order this bounce's queue by (direction octant, origin Morton bucket): three small kernels that read the live count
           // from the wavefront counters -- no host synchronisation.  Primary rays are coherent already.
           ScopedTimer t(ctx, timing, T_SORT);
-          launchSortQueue(st, ctx->view, wf.rayO, wf.rayD, wf.queueCur, sortAlt, wf.counters + 0, (uint32_t)sl.capacity, sl.sortScratch, ctx->numSMs);
+          launchSortQueue(st, ctx->view, wf.rayO, wf.rayD, wf.queueCur, sortAlt, wf.counters + wf.cbase, (uint32_t)sl.capacity, sl.sortScratch, ctx->numSMs);
           std::swap(wf.queueCur, sortAlt);
           ctx->stats.kernel_launches += 3;
         }
         TraceLaunch L{};
-        L.rayO = wf.rayO; L.rayD = wf.rayD; L.queue = wf.queueCur; L.count = wf.counters + 0; L.cursor = wf.counters + 3;
+        L.rayO = wf.rayO; L.rayD = wf.rayD; L.queue = wf.queueCur; L.count = wf.counters + wf.cbase; L.cursor = wf.counters + wf.cbase + 1;
         L.hit = wf.hit; L.stats = dstats; L.cost = heatmap ? wf.sum : nullptr;
         {
           ScopedTimer t(ctx, timing, T_CLOSEST);
@@ -1224,7 +1245,7 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
         }
         TraceLaunch S{};
         S.rayO = wf.shO; S.rayD = wf.shD; S.queue = nullptr;
-        S.count = wf.counters + (wf.shadowSlot ? 5 : 2); S.cursor = wf.counters + (wf.shadowSlot ? 6 : 4);
+        S.count = wf.counters + wf.cbase + 2; S.cursor = wf.counters + wf.cbase + 3; S.primary = depth == 0 ? 1u : 0u;
         S.shC = wf.shC; S.rad = wf.rad; S.stats = dstats; S.cost = heatmap ? wf.sum : nullptr;
         if(overlap)
         {
@@ -1241,23 +1262,23 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
           ScopedTimer t0(ctx, timing && depth == 0, T_SHADOW0);
           launchTraceShadow(st, ctx->view, S, counting, ctx->numSMs);
         }
-        launchSwapQueues(st, wf, dstats, depth == 0);  // device side: counts; host side: the two id arrays
-        std::swap(wf.queueCur, wf.queueNext);
-        ctx->stats.kernel_launches += 4;
+        std::swap(wf.queueCur, wf.queueNext);  // the counts need no swap: every bounce has its own (Wavefront::counters)
+        ctx->stats.kernel_launches += 3;
       }
       if(overlap && state->maxDepth > 0)
         ev(cudaStreamWaitEvent(st, sl.evShadow, 0));
+      if(!fuseFinish)
       {
         ScopedTimer t(ctx, timing, T_ACCUM);
         launchFinishSample(st, wf, fp, ctx->numSMs);
+        ctx->stats.kernel_launches++;
       }
-      ctx->stats.kernel_launches++;
     }
     {
       // the running mean is order dependent (pathtrace.comp:126): batches accumulate in frame order, whichever slot they ran on
       ev(imageBegin(ctx, st));
       ScopedTimer t(ctx, timing, T_ACCUM);
-      launchAccumulate(st, wf, fp, ctx->image, ctx->numSMs);
+      launchAccumulate(st, wf, fp, ctx->image, ctx->numSMs, fuseFinish);
     }
     ev(imageEnd(ctx, st));
     ctx->stats.kernel_launches++;

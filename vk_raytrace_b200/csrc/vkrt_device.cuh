@@ -95,8 +95,12 @@ struct Wavefront
   float4*   shC;       // contribution.xyz, path id bits
   uint32_t* queueCur;  // path ids to process this bounce
   uint32_t* queueNext;
-  uint32_t* counters;  // [0] cur count, [1] next count, [2] shadow count, [3] trace cursor, [4] shadow cursor, [5]/[6] shadow count/cursor of odd bounces
-  uint32_t  shadowSlot;  // bounce parity: which shadow count/cursor pair this bounce uses (the any-hit kernel of bounce b overlaps bounce b+1)
+  // Per bounce d four counters at counters[4 d ..]: [0] paths queued for the closest-hit trace of bounce d (raygen / shade of bounce
+  // d - 1 fill it), [1] its work cursor, [2] shadow rays of bounce d, [3] their cursor.  Raygen zeroes all of them, so nothing has to
+  // be reset or swapped between bounces (round 1 launched a one-thread kernel per bounce for that).
+  uint32_t* counters;
+  uint32_t  cbase;     // 4 x the bounce this launch works on
+  uint32_t  clevels;   // bounces the counter array holds (maxDepth + 1)
   const uint32_t* pixelOfLocal;  // local pixel slot -> y*W + x
   uint32_t  numLocalPixels;
   uint32_t  numPaths;  // numLocalPixels * framesInFlight

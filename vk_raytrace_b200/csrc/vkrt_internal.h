@@ -59,6 +59,7 @@ struct TraceLaunch
   const float4*   shC;
   float4*         rad;
   TraceStats*     stats;      // nullptr unless counting
+  uint32_t        primary;    // shadow resolve: this is bounce 0 (bounce-class statistics)
   float4*         cost;       // heat-map debug mode: per path, .w accumulates the traversal steps of its rays (counting kernels only)
 };
 int  traceBvhWidth(uint32_t numTris);  // 2 or 4: tree the trace kernels walk for a scene of this size (VKRT_BVH_WIDTH)
@@ -84,8 +85,8 @@ void launchShadeFast(cudaStream_t s, const SceneView& scene, const Wavefront& wf
 void launchTailPrecise(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs);
 void launchTailFast(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs);
 void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, int numSMs);
-void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, int numSMs);
-void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats, bool primary);
+// fromRadiance: maxSamples == 1 -- the firefly clamp of finishSample is applied here and that launch is skipped
+void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, int numSMs, bool fromRadiance);
 void launchShardCopy(cudaStream_t s, float4* image, const uint32_t* pixels, uint32_t n, float4* compact, bool toImage);
 struct MipView  // RGBA32F mip pyramid of the accumulation image (level 0 = the image itself)
 {

@@ -35,16 +35,11 @@ __global__ void __launch_bounds__(256) raygenKernel(const __grid_constant__ Scen
                                                     const __grid_constant__ FrameParams fp)
 {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if(p < 4u * wf.clevels)
+    wf.counters[p] = (p == 0) ? wf.numPaths : 0u;  // every bounce's counts and cursors (the wavefront always has >= 4 x levels paths or the loop below covers it)
   if(p == 0)
-  {
-    wf.counters[0] = wf.numPaths;
-    wf.counters[1] = 0;
-    wf.counters[2] = 0;
-    wf.counters[3] = 0;
-    wf.counters[4] = 0;
-    wf.counters[5] = 0;
-    wf.counters[6] = 0;
-  }
+    for(uint32_t k = wf.numPaths; k < 4u * wf.clevels; k++)  // tiny wavefronts: fewer paths than counters
+      wf.counters[k] = 0u;
   if(p >= wf.numPaths)
     return;
   const uint32_t f     = p / wf.numLocalPixels;
@@ -498,7 +493,7 @@ template <int PBR, int FM>  // FM: distinct kernel symbols for the IEEE and the 
 __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
                                                                             const __grid_constant__ FrameParams fp, TraceStats* stats)
 {
-  const uint32_t count = wf.counters[0];
+  const uint32_t count = wf.counters[wf.cbase];
   const uint32_t lane  = threadIdx.x & 31u;
   for(uint32_t base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x)
   {
@@ -538,8 +533,8 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(cons
     uint32_t baseNext = 0, baseSh = 0;
     if(lane == 0)
     {
-      if(mNext) baseNext = atomicAdd(&wf.counters[1], (uint32_t)__popc(mNext));
-      if(mSh) baseSh = atomicAdd(&wf.counters[wf.shadowSlot ? 5 : 2], (uint32_t)__popc(mSh));
+      if(mNext) baseNext = atomicAdd(&wf.counters[wf.cbase + 4], (uint32_t)__popc(mNext));  // the next bounce's queue
+      if(mSh) baseSh = atomicAdd(&wf.counters[wf.cbase + 2], (uint32_t)__popc(mSh));
     }
     baseNext = __shfl_sync(0xffffffffu, baseNext, 0);
     baseSh   = __shfl_sync(0xffffffffu, baseSh, 0);
@@ -572,7 +567,7 @@ template <int PBR, int FM>
 __global__ void __launch_bounds__(128) tailKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
                                                   const __grid_constant__ FrameParams fp0, TraceStats* stats)
 {
-  const uint32_t     count = wf.counters[0];
+  const uint32_t     count = wf.counters[wf.cbase];
   unsigned long long nClosest = 0, nShadow = 0;
   for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
   {
@@ -631,31 +626,6 @@ __global__ void __launch_bounds__(128) tailKernel(const __grid_constant__ SceneV
 }
 
 #ifndef VKRT_FAST_MATH
-// After the shadow pass of a bounce: next -> cur, reset cursors, count shadow rays.
-__global__ void swapQueuesKernel(Wavefront wf, TraceStats* stats, bool primary)
-{
-  if(stats)
-  {
-    atomicAdd(&stats->shadowRays, (unsigned long long)wf.counters[wf.shadowSlot ? 5 : 2]);
-    if(primary)
-      atomicAdd(&stats->shadowRaysPrimary, (unsigned long long)wf.counters[wf.shadowSlot ? 5 : 2]);
-  }
-  wf.counters[0] = wf.counters[1];
-  wf.counters[1] = 0;
-  wf.counters[3] = 0;
-  // this bounce's shadow count/cursor may still be in use by its any-hit kernel: reset the pair of the next bounce
-  if(wf.shadowSlot)
-  {
-    wf.counters[2] = 0;
-    wf.counters[4] = 0;
-  }
-  else
-  {
-    wf.counters[5] = 0;
-    wf.counters[6] = 0;
-  }
-}
-
 // ---- sample finish: firefly clamp (pathtrace.glsl:380-384) + pixel sample sum (pathtrace.comp:102-105) ---
 __global__ void __launch_bounds__(256) finishSampleKernel(const __grid_constant__ Wavefront wf, const __grid_constant__ FrameParams fp)
 {
@@ -692,7 +662,7 @@ constexpr float kHeatNsPerStep = 50.0f;
 
 // ---- accumulate: pathtrace.comp:106,122-133 (running mean, frame order) ------------------------------------
 __global__ void __launch_bounds__(256) accumulateKernel(const __grid_constant__ Wavefront wf, const __grid_constant__ FrameParams fp,
-                                                        float4* __restrict__ image)
+                                                        float4* __restrict__ image, bool fromRadiance)
 {
   const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
   if(lp >= wf.numLocalPixels)
@@ -703,7 +673,18 @@ __global__ void __launch_bounds__(256) accumulateKernel(const __grid_constant__ 
   for(int f = 0; f < fp.framesInBatch; f++)
   {
     const int frame      = fp.state.frame + f;
-    const float4 sum     = wf.sum[(size_t)f * wf.numLocalPixels + lp];
+    float4 sum;
+    if(fromRadiance)
+    {
+      // one sample per frame: finishSampleKernel's work, same operations (firefly clamp, 0 + radiance as the sample sum)
+      float3 radiance = f3(wf.rad[(size_t)f * wf.numLocalPixels + lp]);
+      float  lum      = dot(radiance, f3(0.212671f, 0.715160f, 0.072169f));
+      if(lum > fp.state.fireflyClampThreshold)
+        radiance *= fp.state.fireflyClampThreshold / lum;
+      sum = f4(0.0f + radiance.x, 0.0f + radiance.y, 0.0f + radiance.z, 0.0f);
+    }
+    else
+      sum = wf.sum[(size_t)f * wf.numLocalPixels + lp];
     float3       pixelColor = f3(sum);
     pixelColor /= (float)fp.state.maxSamples;
     if(fp.state.debugging_mode == VKRT_DBG_HEATMAP)
@@ -892,7 +873,6 @@ void VKRT_LAUNCH_TAIL(cudaStream_t s, const SceneView& scene, const Wavefront& w
     launchTailT<1>(s, scene, wf, fp, stats, numSMs);
 }
 #ifndef VKRT_FAST_MATH
-void launchSwapQueues(cudaStream_t s, const Wavefront& wf, TraceStats* stats, bool primary) { swapQueuesKernel<<<1, 1, 0, s>>>(wf, stats, primary); }
 // tile shards: image[pixels[i]] <-> compact[i] (multi-GPU exchange of owned pixels instead of a full-image reduce)
 __global__ void __launch_bounds__(256) shardCopyKernel(float4* __restrict__ image, const uint32_t* __restrict__ pixels, uint32_t n,
                                                        float4* __restrict__ compact, bool toImage)
@@ -914,9 +894,9 @@ void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& 
 {
   finishSampleKernel<<<(wf.numPaths + 255) / 256, 256, 0, s>>>(wf, fp);
 }
-void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, int)
+void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, int, bool fromRadiance)
 {
-  accumulateKernel<<<(wf.numLocalPixels + 255) / 256, 256, 0, s>>>(wf, fp, image);
+  accumulateKernel<<<(wf.numLocalPixels + 255) / 256, 256, 0, s>>>(wf, fp, image, fromRadiance);
 }
 void launchMipDown(cudaStream_t s, const float4* src, int sw, int sh, float4* dst, int dw, int dh)
 {

@@ -122,6 +122,12 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
   uint32_t* const sstack = &s_stack[threadIdx.x];
   uint32_t        lstack[kStackLocal];
   const uint32_t  n    = *L.count;
+  if(MODE == MODE_SHADOW_RESOLVE && L.stats && blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    atomicAdd(&L.stats->shadowRays, (unsigned long long)n);  // AnyHit() calls of this bounce (round 1 counted them in a kernel of their own)
+    if(L.primary)
+      atomicAdd(&L.stats->shadowRaysPrimary, (unsigned long long)n);
+  }
   const uint32_t  lane = threadIdx.x & 31u;
   const unsigned  lt   = (1u << lane) - 1u;
 
@@ -579,6 +585,12 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_WIDE_MINBLOCKS) traceKernelW
   uint32_t* const sstack = &s_stack[threadIdx.x];
   uint32_t        lstack[kStackLocal];
   const uint32_t  n    = *L.count;
+  if(MODE == MODE_SHADOW_RESOLVE && L.stats && blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    atomicAdd(&L.stats->shadowRays, (unsigned long long)n);  // AnyHit() calls of this bounce (round 1 counted them in a kernel of their own)
+    if(L.primary)
+      atomicAdd(&L.stats->shadowRaysPrimary, (unsigned long long)n);
+  }
   const uint32_t  lane = threadIdx.x & 31u;
 
   if(sc.numTris == 0)
@@ -864,6 +876,12 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernelIfIf(const __grid_c
   uint32_t* const sstack = &s_stack[threadIdx.x];
   uint32_t        lstack[kStackLocal];
   const uint32_t  n    = *L.count;
+  if(MODE == MODE_SHADOW_RESOLVE && L.stats && blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    atomicAdd(&L.stats->shadowRays, (unsigned long long)n);  // AnyHit() calls of this bounce (round 1 counted them in a kernel of their own)
+    if(L.primary)
+      atomicAdd(&L.stats->shadowRaysPrimary, (unsigned long long)n);
+  }
   const uint32_t  lane = threadIdx.x & 31u;
   const unsigned  lt   = (1u << lane) - 1u;
 
@@ -1107,6 +1125,12 @@ __global__ void __launch_bounds__(kTraceBlock, 8) traceKernelCoop(const __grid_c
   WarpShared&     ws     = s_ws[threadIdx.x >> 5];
   uint32_t        lstack[kStackLocal];
   const uint32_t  n    = *L.count;
+  if(MODE == MODE_SHADOW_RESOLVE && L.stats && blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    atomicAdd(&L.stats->shadowRays, (unsigned long long)n);  // AnyHit() calls of this bounce (round 1 counted them in a kernel of their own)
+    if(L.primary)
+      atomicAdd(&L.stats->shadowRaysPrimary, (unsigned long long)n);
+  }
   const uint32_t  lane = threadIdx.x & 31u;
   const unsigned  lt   = (1u << lane) - 1u;
 
