@@ -301,44 +301,56 @@ def _temperature(v):
 
 
 def test_heatmap_debug_mode(vk, gpu):
-    """Debug mode 12 (pathtrace.comp:108-117): the reference maps the invocation's nanoseconds through temperature(); the wavefront
-    stand-in maps the pixel's traversal work (nodes + triangles of all its rays, 50 ns nominal per step).  Checked: the colour map,
-    the range handling, run-to-run stability, and that the work adds up to the device counters."""
+    """Debug mode 12 (pathtrace.comp:108-117): the reference maps the nanoseconds its invocation took through temperature(); the
+    wavefront kernels add the nanoseconds (%globaltimer) a lane held each path -- traversal of its rays, shading of its bounces.
+    Like any clock it is not reproducible; checked: the colour map, the range handling, that the measure is a time (sky pixels, whose
+    paths end at the first miss, are cheaper than geometry; two runs agree on the picture) and that it leaves the renderer intact."""
     from vk_raytrace_b200 import structs as S
     W, H = 160, 96
     vk.upload_scene(gpu, small_sponza(), W, H)
-    gpu.reset_stats()
-    st = S.default_rtx_state(W, H, maxDepth=5, debugging_mode=12, minHeatmap=0, maxHeatmap=65000)
+    hi = 4_000_000          # ns: a latency-bound wavefront keeps a path far longer than an RT-core invocation (reference default 65 us)
+    st = S.default_rtx_state(W, H, maxDepth=5, debugging_mode=12, minHeatmap=0, maxHeatmap=hi)
     gpu.render(st, 1)
     a = gpu.output_read()[..., :3]
-    s = gpu.stats()
     gpu.output_clear()
     gpu.render(st, 1)
-    # like the reference's clock the measure is not bit-reproducible: how far a lane descends speculatively while a leaf is parked
-    # depends on the other rays of its warp, which depends on the dynamic ray fetch.  Two runs agree closely, not exactly.
     b = gpu.output_read()[..., :3]
-    assert np.isfinite(a).all() and np.abs(a - b).mean() < 0.02
+    assert np.isfinite(a).all() and np.isfinite(b).all()
     # every pixel is a point of the temperature curve: recover the intensity from the (piecewise unique) colour and re-evaluate
     grid = np.linspace(0.0, 1.0, 20001)
     lut = _temperature(grid)
-    flat = a.reshape(-1, 3).astype(np.float64)
-    idx = np.array([np.argmin(((lut - c) ** 2).sum(1)) for c in flat[::7]])
-    assert np.abs(lut[idx] - flat[::7]).max() < 2e-3
-    val = grid[idx]
-    assert val.min() < 0.05 and val.max() > 0.15 and len(np.unique(np.round(val, 3))) > 20     # sky pixels are cheap, geometry is not
-    # total work = the counters of the same run (one sample per pixel, one frame)
-    steps = float(s.nodes_visited + s.tris_tested)
-    assert steps > 0
-    inside = val < 0.999
-    est = (val * 65000.0 / 50.0)
-    if inside.all():
-        assert abs(est.sum() * 7 - steps) / steps < 0.1
+
+    def intensity(img):
+        flat = img.reshape(-1, 3).astype(np.float64)[::7]
+        idx = np.array([np.argmin(((lut - c) ** 2).sum(1)) for c in flat])
+        assert np.abs(lut[idx] - flat).max() < 2e-3
+        return grid[idx]
+    va, vb = intensity(a), intensity(b)
+    assert va.max() > va.min() and len(np.unique(np.round(va, 3))) > 20          # a distribution, not a constant
+    assert np.corrcoef(va, vb)[0, 1] > 0.5                                        # two runs: the same picture, not the same numbers
+    # a time: paths that leave through the open roof at the first bounce cost less than paths that bounce around inside.
+    # Reference picture: radiance debug view at depth 1 is black exactly where the primary ray missed everything.
+    gpu.output_clear()
+    gpu.render(S.default_rtx_state(W, H, maxDepth=1, debugging_mode=5), 1)        # alpha view: 0 on a miss, 1 on geometry
+    hit = (gpu.output_read()[..., 0].reshape(-1)[::7] > 0.5)
+    if hit.any() and (~hit).any():
+        assert va[~hit].mean() < va[hit].mean()
     # range handling: everything below min -> temperature(0) = blue, everything above max -> temperature(1) = red
-    for lo, hi, want in ((10_000_000, 20_000_000, (0.0, 0.0, 1.0)), (0, 1, (1.0, 0.0, 0.0))):
+    for lo, hi2, want in ((1_000_000_000, 2_000_000_000, (0.0, 0.0, 1.0)), (0, 1, (1.0, 0.0, 0.0))):
         gpu.output_clear()
-        gpu.render(S.default_rtx_state(W, H, maxDepth=5, debugging_mode=12, minHeatmap=lo, maxHeatmap=hi), 1)
+        gpu.render(S.default_rtx_state(W, H, maxDepth=5, debugging_mode=12, minHeatmap=lo, maxHeatmap=hi2), 1)
         img = gpu.output_read()[..., :3]
         assert np.abs(img - np.array(want, np.float32)).max() < 1e-6
+    # the renderer is untouched by the instrumentation: a normal render afterwards equals one before
+    st0 = S.default_rtx_state(W, H, maxDepth=5)
+    gpu.output_clear()
+    gpu.render(st0, 2)
+    ref = gpu.output_read()
+    gpu.output_clear()
+    gpu.render(st, 1)
+    gpu.output_clear()
+    gpu.render(st0, 2)
+    assert np.array_equal(gpu.output_read(), ref)
 
 
 @pytest.mark.parametrize("build_mode", [0, 1, 3, 4])

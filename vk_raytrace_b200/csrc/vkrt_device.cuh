@@ -131,6 +131,15 @@ VKRT_D void stS(T* p, T v)
 #endif
 }
 
+// nanosecond timer of the device (PTX %globaltimer, low word): what the heat-map debug view measures per path, like the
+// reference's clockRealtimeEXT around its per-pixel loop (shaders/pathtrace.comp:89,108-117)
+VKRT_D uint32_t deviceNs()
+{
+  uint32_t t;
+  asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t));
+  return t;
+}
+
 struct TraceStats  // device counters
 {
   unsigned long long closestRays, shadowRays, nodesVisited, trisTested, shadowNodes, shadowTris, shadowRaysPrimary;

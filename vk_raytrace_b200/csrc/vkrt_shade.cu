@@ -489,7 +489,7 @@ VKRT_D void bouncePhaseSample(const SceneView& sc, const FrameParams& fp, Bounce
   out.wantNext = (depth + 1 < maxDepth);
 }
 
-template <int PBR, int FM>  // FM: distinct kernel symbols for the IEEE and the fast-math build of this file
+template <int PBR, int FM, bool HEAT>  // FM: distinct kernel symbols for the IEEE and the fast-math build of this file; HEAT: debug mode 12 (times every path)
 __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
                                                                             const __grid_constant__ FrameParams fp, TraceStats* stats)
 {
@@ -499,6 +499,7 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(cons
   {
     const uint32_t i     = base + threadIdx.x;
     const bool     valid = i < count;
+    const uint32_t t0    = HEAT ? deviceNs() : 0u;
     ShadeOut       out;
     out.wantNext = out.wantShadow = false;
     uint32_t    p = 0;
@@ -526,6 +527,8 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(cons
       stS(&wf.thr[p], f4(b.throughput, __uint_as_float(b.seed)));
       stS(&wf.rad[p], f4(b.radiance, 0.f));
       stS(&wf.absb[p], f4(b.absorption, 0.f));
+      if(HEAT)
+        wf.sum[p].w += (float)(deviceNs() - t0);  // heat map: the shading time of this bounce joins the traversal time of its rays
     }
     // warp-aggregated queue appends (all 32 lanes reach this point)
     const unsigned mNext = __ballot_sync(0xffffffffu, out.wantNext);
@@ -654,11 +657,10 @@ VKRT_D float3 temperature(float intensity)
          + f3(1.f, 0.f, 0.f) * smoothstepf(0.75f, 1.0f, intensity);
 }
 // The reference colours a pixel by the nanoseconds its invocation took (clockRealtimeEXT around the sample loop,
-// pathtrace.comp:89,108-117).  A wavefront has no per-pixel clock; the deterministic stand-in is the traversal work of the
-// pixel's rays -- BVH nodes visited + triangles tested over all samples and bounces -- at a nominal 50 ns per step, so that the
-// reference's default range [0, 65000] covers 1300 steps.  Like a clock it is not bit-reproducible from run to run: how far a lane
-// descends speculatively while a leaf is parked depends on the other rays in its warp.
-constexpr float kHeatNsPerStep = 50.0f;
+// pathtrace.comp:89,108-117).  The wavefront equivalent: every kernel that works on a path adds the nanoseconds (%globaltimer) its
+// lane held that path -- traversal of its closest and shadow rays (waiting for the rest of the warp included, as a megakernel
+// invocation waits for its neighbours) and the shading of each bounce -- to the path's cost, and the accumulate kernel maps the sum
+// through the reference's temperature() and min/maxHeatmap.  Like any clock it is not reproducible from run to run.
 
 // ---- accumulate: pathtrace.comp:106,122-133 (running mean, frame order) ------------------------------------
 __global__ void __launch_bounds__(256) accumulateKernel(const __grid_constant__ Wavefront wf, const __grid_constant__ FrameParams fp,
@@ -690,7 +692,7 @@ __global__ void __launch_bounds__(256) accumulateKernel(const __grid_constant__ 
     if(fp.state.debugging_mode == VKRT_DBG_HEATMAP)
     {
       const float low = (float)fp.state.minHeatmap, high = (float)fp.state.maxHeatmap;
-      pixelColor      = temperature(clampf((sum.w * kHeatNsPerStep - low) / (high - low), 0.0f, 1.0f));
+      pixelColor      = temperature(clampf((sum.w - low) / (high - low), 0.0f, 1.0f));
     }
     if(frame > 0)
       acc = mix(acc, pixelColor, 1.0f / (float)(frame + 1));
@@ -831,28 +833,29 @@ void launchRaygen(cudaStream_t s, const SceneView& scene, const Wavefront& wf, c
   raygenKernel<<<(wf.numPaths + 255) / 256, 256, 0, s>>>(scene, wf, fp);
 }
 #endif
-template <int PBR>
+template <int PBR, bool HEAT>
 static void launchShadeT(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs)
 {
   static int perSM = 0;
   if(!perSM)
   {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shadeKernel<PBR, VKRT_SHADE_FM>, kShadeBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, shadeKernel<PBR, VKRT_SHADE_FM, HEAT>, kShadeBlock, 0);
     if(perSM < 1) perSM = 1;
   }
   int grid = numSMs * perSM;
   int need = (int)((wf.numPaths + kShadeBlock - 1) / kShadeBlock);
   if(grid > need) grid = need;
   if(grid < 1) grid = 1;
-  shadeKernel<PBR, VKRT_SHADE_FM><<<grid, kShadeBlock, 0, s>>>(scene, wf, fp, stats);
+  shadeKernel<PBR, VKRT_SHADE_FM, HEAT><<<grid, kShadeBlock, 0, s>>>(scene, wf, fp, stats);
 }
 void VKRT_LAUNCH_SHADE(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs)
 {
   // one kernel per BSDF model (RtxState.pbrMode, pathtrace.glsl:40-56): halves the code and register pressure
+  const bool heat = fp.state.debugging_mode == VKRT_DBG_HEATMAP;  // the timed variant (debug mode 12) is a kernel of its own
   if(fp.state.pbrMode == 0)
-    launchShadeT<0>(s, scene, wf, fp, stats, numSMs);
+    heat ? launchShadeT<0, true>(s, scene, wf, fp, stats, numSMs) : launchShadeT<0, false>(s, scene, wf, fp, stats, numSMs);
   else
-    launchShadeT<1>(s, scene, wf, fp, stats, numSMs);
+    heat ? launchShadeT<1, true>(s, scene, wf, fp, stats, numSMs) : launchShadeT<1, false>(s, scene, wf, fp, stats, numSMs);
 }
 template <int PBR>
 static void launchTailT(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs)

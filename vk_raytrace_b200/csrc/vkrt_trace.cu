@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
           bestT   = tmax; bestU = 0.f; bestV = 0.f; bestTri = ~0u;
           node    = 0; leaf = 0; sp = 0;
           haveRay = true;
-          rayBase = nNodes + nTris;
+          rayBase = (COUNT && L.cost) ? deviceNs() : 0u;  // heat map: when this lane took the ray
           if(QN)
           {
             // the ray in grid space; its origin is moved to (just before) the entry into the grid cube so that
@@ -538,9 +538,10 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_TRACE_MINBLOCKS) traceKernel
       {
         if(COUNT && L.cost && MODE != MODE_ANY_PROBE)
         {
-          // heat-map debug mode: the work this ray cost, charged to its path (one closest and one shadow ray per path and launch)
+          // heat-map debug mode: the nanoseconds this lane held the ray (waiting for the other lanes of its warp included, as in the
+          // reference's per-invocation clock), charged to its path (one closest and one shadow ray per path and launch)
           const uint32_t path = (MODE == MODE_SHADOW_RESOLVE) ? __float_as_uint(L.shC[slot].w) : slot;
-          L.cost[path].w += (float)(nNodes + nTris - rayBase);
+          L.cost[path].w += (float)(deviceNs() - rayBase);
         }
         if(MODE == MODE_CLOSEST)
           stS(&L.hit[slot], (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(bestT, bestU, bestV, __uint_as_float(bestTri)));
@@ -665,7 +666,7 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_WIDE_MINBLOCKS) traceKernelW
           bestT   = tmax; bestU = 0.f; bestV = 0.f; bestTri = ~0u;
           node    = 0; leaf = 0; sp = 0;
           haveRay = true;
-          rayBase = nNodes + nTris;
+          rayBase = (COUNT && L.cost) ? deviceNs() : 0u;  // heat map: when this lane took the ray
           // grid-space ray, see traceKernel<QN>
           const float3 dg = d * sc.gridInv;
           id              = f3(safeInv(dg.x), safeInv(dg.y), safeInv(dg.z));
@@ -836,9 +837,10 @@ __global__ void __launch_bounds__(kTraceBlock, VKRT_WIDE_MINBLOCKS) traceKernelW
       {
         if(COUNT && L.cost && MODE != MODE_ANY_PROBE)
         {
-          // heat-map debug mode: the work this ray cost, charged to its path (one closest and one shadow ray per path and launch)
+          // heat-map debug mode: the nanoseconds this lane held the ray (waiting for the other lanes of its warp included, as in the
+          // reference's per-invocation clock), charged to its path (one closest and one shadow ray per path and launch)
           const uint32_t path = (MODE == MODE_SHADOW_RESOLVE) ? __float_as_uint(L.shC[slot].w) : slot;
-          L.cost[path].w += (float)(nNodes + nTris - rayBase);
+          L.cost[path].w += (float)(deviceNs() - rayBase);
         }
         if(MODE == MODE_CLOSEST)
           stS(&L.hit[slot], (bestTri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(bestT, bestU, bestV, __uint_as_float(bestTri)));
