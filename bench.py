@@ -483,14 +483,15 @@ def main():
     # ---- e2e: the same metric through the C ABI as an interactive host drives it, one definition for every N: per step a host
     #      SceneCamera goes in, ONE frame is rendered (sharded when N > 1, then exchanged), and the tonemapped RGBA8 frame comes
     #      back to page-locked host memory on rank 0.  The read-back of frame f overlaps the rendering of frame f+1
-    #      (vkrt_tonemap_async, two staging buffers), as a display loop does.
+    #      (vkrt_tonemap_async, a ring of staging buffers), as a display loop does.
     e2e = None
     if not args.no_e2e:
         cam = scene.camera
         tm = S.default_tonemapper()
-        bufs = [ctx.host_alloc((H, W, 4)), ctx.host_alloc((H, W, 4))] if rank == 0 else None
+        nbuf = 4    # staging ring: the host may run this many frames ahead of the copies (the library has four staging slots)
+        bufs = [ctx.host_alloc((H, W, 4)) for _ in range(nbuf)] if rank == 0 else None
         opts_e = make_opts()
-        k = max(4, min(args.steps, 16))
+        k = max(4, min(args.steps, 32))
         ex = m["ex"]
         nl = 0 if scene.lights is None else len(scene.lights)
 
@@ -502,22 +503,23 @@ def main():
             if ex:
                 ex.run()
             if rank == 0:
-                ctx.tonemap_wait(f & 1)     # the copy that last used this staging slot (frame f-2)
-                ctx.tonemap_async(tm, bufs[f & 1], f & 1)   # D2H: the displayed RGBA8 frame
+                ctx.tonemap_wait(f % nbuf)     # the copy that last used this staging slot (frame f - nbuf)
+                ctx.tonemap_async(tm, bufs[f % nbuf], f % nbuf)   # D2H: the displayed RGBA8 frame
 
-        for f in range(2):
+        def drain():
+            if rank == 0:
+                for b in range(nbuf):
+                    ctx.tonemap_wait(b)
+
+        for f in range(nbuf):
             step(f)
-        if rank == 0:
-            ctx.tonemap_wait(0)
-            ctx.tonemap_wait(1)
+        drain()
         ctx.reset_stats()
         barrier()
         t0 = time.time()
         for f in range(k):
-            step(2 + f)
-        if rank == 0:
-            ctx.tonemap_wait(0)
-            ctx.tonemap_wait(1)
+            step(nbuf + f)
+        drain()
         ctx.sync()
         barrier()
         dt = time.time() - t0
@@ -530,7 +532,7 @@ def main():
         e2e = {"value": er / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 140 + 48, "d2h_bytes_per_step": W * H * 4, "steps": k,
                "ms_per_step": dt / k * 1e3,
                "what": "per step: vkrt_set_camera(host SceneCamera) + vkrt_render(1 frame%s) + vkrt_tonemap_async -> page-locked host RGBA8 on "
-                       "rank 0; frame f's read-back overlaps frame f+1 (two staging buffers, two wavefront slots); wall clock over %d steps "
+                       "rank 0; frame f's read-back overlaps the frames after it (ring of four staging buffers, rotating wavefront slots); wall clock over %d steps "
                        "including the final waits" % (", tile shard + gather to rank 0" if use_dist else "", k)}
         if rank == 0:
             for b in bufs:

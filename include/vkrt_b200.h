@@ -175,7 +175,7 @@ int vkrt_tonemap(vkrt_ctx* ctx, const Tonemapper* tonemapper, uint8_t* host_rgba
 int vkrt_tonemap_float(vkrt_ctx* ctx, const Tonemapper* tonemapper, float* host_rgba32f);
 /* The display path of an interactive host (src/sample_example.cpp:417-426 renders frame f+1 while frame f is presented):
  * tonemap the image as it is after the frames enqueued so far and copy the RGBA8 result to `host_rgba8` WITHOUT waiting --
- * the copy overlaps the next vkrt_render.  `slot` (0 or 1) names one of two device staging buffers; the host buffer
+ * the copy overlaps the next vkrt_render.  `slot` (0..3) names one of four device staging buffers; the host buffer
  * must stay valid (and should be page-locked: vkrt_host_alloc) until vkrt_tonemap_wait(ctx, slot) returns. */
 int vkrt_tonemap_async(vkrt_ctx* ctx, const Tonemapper* tonemapper, uint8_t* host_rgba8, int32_t slot);
 int vkrt_tonemap_wait(vkrt_ctx* ctx, int32_t slot);

@@ -12,10 +12,10 @@ W, H = cfg["w"], cfg["h"]
 scene = bench.make_scene(cfg)
 ctx = Context(0)
 upload_scene(ctx, scene, W, H, build_mode=4)
-print("dual_slot env:", os.environ.get("VKRT_DUAL_SLOT", "default(1)"))
-for shards in (8, 4, 1):
-    for tail in (0, -1, 2):
-        for fif in (20, 10, 40):
+print("dual_slot env:", os.environ.get("VKRT_DUAL_SLOT", "default(1)"), "slots env:", os.environ.get("VKRT_SLOTS", "default(2)"))
+for shards in [int(x) for x in os.environ.get("SHARD_PROBE_SHARDS", "8,4,1").split(",")]:
+    for tail in [int(x) for x in os.environ.get("SHARD_PROBE_TAILS", "0,-1,2").split(",")]:
+        for fif in [int(x) for x in os.environ.get("SHARD_PROBE_FIFS", "20,10,40").split(",")]:
             st = S.default_rtx_state(W, H, maxDepth=8)
             o = S.RenderOpts()
             o.shard_rank, o.shard_count, o.tile_size, o.tail_from, o.frames_in_flight = 0, shards, 64, tail, fif

@@ -640,7 +640,7 @@ def test_converged_whole_image(vk, ob, gpu, which, precise, pbr):
 
 def test_async_tonemap_dual_slots_and_shard_exchange(vk, gpu):
     """Round-2 entry points: (1) vkrt_tonemap_async / _wait into page-locked memory gives the bytes of vkrt_tonemap, also while the
-    next frame is already rendering on the other wavefront slot; (2) one-frame calls alternating between the two slots give the
+    next frames are already rendering on other wavefront slots; (2) one-frame calls rotating through the slots give the
     image of one batched call, bit for bit; (3) pack_shard on N 'ranks' + unpack_shard on the root rebuilds the unsharded image."""
     import torch
     from vk_raytrace_b200 import structs as S
@@ -671,6 +671,28 @@ def test_async_tonemap_dual_slots_and_shard_exchange(vk, gpu):
         gpu.render(S.default_rtx_state(W, H, maxDepth=5, frame=f), 1)
         assert np.array_equal(frames8[f], gpu.tonemap(tm)), f
     for b in bufs:
+        gpu.host_free(b)
+    # the same loop four frames deep: a ring of four staging slots, one-frame calls rotating through four wavefront slots
+    ring = [gpu.host_alloc((H, W, 4)) for _ in range(4)]
+    gpu.output_clear()
+    got = {}
+    for f in range(10):
+        gpu.render(S.default_rtx_state(W, H, maxDepth=5, frame=f), 1, sync=False)
+        gpu.tonemap_wait(f % 4)
+        if f >= 4:
+            got[f - 4] = ring[f % 4].copy()
+        gpu.tonemap_async(tm, ring[f % 4], f % 4)
+    for k in range(4):
+        gpu.tonemap_wait(k)
+    for f in range(6, 10):
+        got[f] = ring[f % 4].copy()
+    gpu.output_clear()
+    for f in range(10):
+        gpu.render(S.default_rtx_state(W, H, maxDepth=5, frame=f), 1)
+        assert np.array_equal(got[f], gpu.tonemap(tm)), f
+    with pytest.raises(Exception):
+        gpu.tonemap_async(tm, ring[0], 4)                    # only slots 0..3 exist
+    for b in ring:
         gpu.host_free(b)
     # (3) shards
     total = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda:0")

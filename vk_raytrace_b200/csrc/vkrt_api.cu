@@ -44,6 +44,9 @@ enum TimerSlot { T_RAYGEN = 0, T_CLOSEST, T_SHADOW, T_SHADE, T_SORT, T_ACCUM, T_
 // bounce) and the events that order them.  A context owns two: consecutive batches -- the halves of a multi-frame render, or
 // consecutive one-frame calls of an interactive host -- alternate between them, so that the tail of every persistent kernel of
 // one wavefront is filled by kernels of the other (round 1 measured one frame per call at half the batched rate: 16 tails).
+constexpr int kMaxSlots  = 4;  // wavefront slots a context can rotate through
+constexpr int kToneSlots = 4;  // staging buffers of vkrt_tonemap_async
+
 struct WfSlot
 {
   Wavefront    wf{};
@@ -62,8 +65,12 @@ struct vkrt_ctx
   int          device = 0;
   cudaStream_t stream = nullptr;   // == slots[0].s: scene upload, image operations of the synchronous entry points, marks
   cudaStream_t post = nullptr;     // asynchronous tonemap + read-back
-  WfSlot       slots[2];
-  uint32_t     nextSlot = 0;       // batches alternate between the slots, across calls too
+  WfSlot       slots[kMaxSlots];
+  // Slots the renderer rotates through.  A multi-frame call is split into `numSlots` batches: 2 measured best (3: -0.2 %, 4: -0.7 %
+  // -- smaller wavefronts cost more than the extra overlap gains).  One-frame calls of an interactive host take the next of
+  // `numSlotsInteractive` slots, so that many frames overlap: 4 measured +3 % over 2 (profiles/README.md).  VKRT_SLOTS / VKRT_SLOTS_INTERACTIVE.
+  int          numSlots = 2, numSlotsInteractive = 4;
+  uint32_t     nextSlot = 0;       // batches take the slots in turn, across calls too
   cudaEvent_t  evImage = nullptr;  // last operation that touched the accumulation image (accumulate, clear, tonemap, read)
   bool         imagePending = false;
   cudaEvent_t  evFork = nullptr;
@@ -102,9 +109,9 @@ struct vkrt_ctx
   int     W = 0, H = 0;
   float4* dToneF = nullptr;
   uchar4* dTone8 = nullptr;
-  uchar4* dTone8Async[2] = {nullptr, nullptr};  // staging of vkrt_tonemap_async
-  cudaEvent_t evCopy[2] = {nullptr, nullptr};
-  bool    copyPending[2] = {false, false};
+  uchar4* dTone8Async[kToneSlots] = {};  // staging of vkrt_tonemap_async
+  cudaEvent_t evCopy[kToneSlots] = {};
+  bool    copyPending[kToneSlots] = {};
   float4* dMips = nullptr;  // auto-exposure mip pyramid (levels 1..n)
   size_t  mipCapacity = 0;
 
@@ -326,8 +333,14 @@ int vkrt_create(int cuda_device, vkrt_ctx** out_ctx)
       ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
   }
   ok = ok && cudaStreamCreateWithFlags(&ctx->post, cudaStreamNonBlocking) == cudaSuccess;
-  for(cudaEvent_t* e : {&ctx->evImage, &ctx->evFork, &ctx->evCopy[0], &ctx->evCopy[1]})
+  for(cudaEvent_t* e : {&ctx->evImage, &ctx->evFork})
     ok = ok && cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess;
+  for(cudaEvent_t& e : ctx->evCopy)
+    ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+  if(const char* e = getenv("VKRT_SLOTS"))
+    ctx->numSlots = std::max(1, std::min(kMaxSlots, atoi(e)));
+  if(const char* e = getenv("VKRT_SLOTS_INTERACTIVE"))
+    ctx->numSlotsInteractive = std::max(1, std::min(kMaxSlots, atoi(e)));
   if(!ok)
   {
     delete ctx;  // the process is about to report the failure; the few handles created so far go with it
@@ -378,7 +391,8 @@ int vkrt_destroy(vkrt_ctx* ctx)
   cudaFree(ctx->dEnv); cudaFree(ctx->dEnvAccel);
   for(auto& l : ctx->shardLists) cudaFree(l.d);
   if(ctx->ownsImage) cudaFree(ctx->image);
-  cudaFree(ctx->dToneF); cudaFree(ctx->dTone8); cudaFree(ctx->dTone8Async[0]); cudaFree(ctx->dTone8Async[1]); cudaFree(ctx->dMips);
+  cudaFree(ctx->dToneF); cudaFree(ctx->dTone8); cudaFree(ctx->dMips);
+  for(uchar4* b : ctx->dTone8Async) cudaFree(b);
   cudaFree(ctx->dStats);
   cudaFree(ctx->dProbe);
   for(auto& sl : ctx->slots)
@@ -387,7 +401,8 @@ int vkrt_destroy(vkrt_ctx* ctx)
     cudaStreamDestroy(sl.s2);
     cudaStreamDestroy(sl.s);
   }
-  for(cudaEvent_t e : {ctx->evImage, ctx->evFork, ctx->evCopy[0], ctx->evCopy[1]}) cudaEventDestroy(e);
+  for(cudaEvent_t e : {ctx->evImage, ctx->evFork}) cudaEventDestroy(e);
+  for(cudaEvent_t e : ctx->evCopy) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->post);
   delete ctx;
   return VKRT_OK;
@@ -775,10 +790,11 @@ int vkrt_output_create(vkrt_ctx* ctx, uint32_t width, uint32_t height, void* dev
   cudaSetDevice(ctx->device);
   syncAll(ctx);
   ctx->imagePending = false;
-  ctx->copyPending[0] = ctx->copyPending[1] = false;
+  for(bool& b : ctx->copyPending) b = false;
   if(ctx->ownsImage) cudaFree(ctx->image);
-  cudaFree(ctx->dToneF); cudaFree(ctx->dTone8); cudaFree(ctx->dTone8Async[0]); cudaFree(ctx->dTone8Async[1]);
-  ctx->image = nullptr; ctx->dToneF = nullptr; ctx->dTone8 = nullptr; ctx->dTone8Async[0] = ctx->dTone8Async[1] = nullptr;
+  cudaFree(ctx->dToneF); cudaFree(ctx->dTone8);
+  for(uchar4*& b : ctx->dTone8Async) { cudaFree(b); b = nullptr; }
+  ctx->image = nullptr; ctx->dToneF = nullptr; ctx->dTone8 = nullptr;
   ctx->W = (int)width; ctx->H = (int)height;
   if(device_rgba32f)
   {
@@ -886,7 +902,7 @@ int vkrt_tonemap_float(vkrt_ctx* ctx, const Tonemapper* tm, float* host_rgba32f)
 
 int vkrt_tonemap_async(vkrt_ctx* ctx, const Tonemapper* tm, uint8_t* host_rgba8, int32_t slot)
 {
-  if(!ctx || !tm || !host_rgba8 || slot < 0 || slot > 1) return VKRT_ERR_INVALID;
+  if(!ctx || !tm || !host_rgba8 || slot < 0 || slot >= kToneSlots) return VKRT_ERR_INVALID;
   if(!ctx->image) return fail(ctx, VKRT_ERR_STATE, "tonemap_async: no output image");
   cudaSetDevice(ctx->device);
   const size_t n = (size_t)ctx->W * ctx->H;
@@ -905,7 +921,7 @@ int vkrt_tonemap_async(vkrt_ctx* ctx, const Tonemapper* tm, uint8_t* host_rgba8,
 
 int vkrt_tonemap_wait(vkrt_ctx* ctx, int32_t slot)
 {
-  if(!ctx || slot < 0 || slot > 1) return VKRT_ERR_INVALID;
+  if(!ctx || slot < 0 || slot >= kToneSlots) return VKRT_ERR_INVALID;
   cudaSetDevice(ctx->device);
   if(ctx->copyPending[slot])
   {
@@ -1095,7 +1111,7 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
   const bool counting = o.count_traversal != 0 || heatmap;
   const bool timing   = o.profile != 0;  // per-kernel CUDA-event timing
   // per-kernel timing needs the kernels one after the other; otherwise shadow(b) overlaps closest(b+1) on a second stream and
-  // consecutive batches alternate between the two wavefront slots
+  // consecutive batches rotate through the wavefront slots
   static const bool overlapEnv = []() { const char* e = getenv("VKRT_OVERLAP"); return !e || atoi(e) != 0; }();
   static const bool dualEnv    = []() { const char* e = getenv("VKRT_DUAL_SLOT"); return !e || atoi(e) != 0; }();
   const bool overlap  = overlapEnv && !timing && !heatmap;
@@ -1117,17 +1133,18 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
   const bool autoFif = fif <= 0;
   if(autoFif)
   {
-    // automatic: ~64 M paths in flight (11 GB of wavefront state over the two slots) amortise the latency floor of thin late
+    // automatic: ~64 M paths in flight (11 GB of wavefront state over the slots) amortise the latency floor of thin late
     // bounces -- but never more frames than this call renders (a single interactive frame allocates for one frame), and
     // never more than half of the memory that is free right now (168 bytes of wavefront state per path, + 12 with the ray sort)
     fif = (int)std::max<size_t>(1, std::min<size_t>(64, (size_t)(64u << 20) / nLocal));
     fif = std::min(fif, num_frames);
   }
-  // with two slots a batch is half of the frames in flight, so that at least two batches exist to overlap
-  int perBatch = fif;
-  if(dual && std::min(fif, num_frames) >= 2)
-    perBatch = (std::min(fif, num_frames) + 1) / 2;
-  const int slotsNow = (dual && num_frames > perBatch) ? 2 : 1;  // slots this call fills (a one-frame call fills one; the next call the other)
+  // with n slots a batch is 1/n of the frames in flight, so that n batches exist to overlap
+  const int nSlots   = dual ? (num_frames == 1 ? ctx->numSlotsInteractive : ctx->numSlots) : 1;
+  int       perBatch = fif;
+  if(nSlots > 1 && std::min(fif, num_frames) >= 2)
+    perBatch = (std::min(fif, num_frames) + nSlots - 1) / nSlots;
+  const int slotsNow = std::min(nSlots, (num_frames + perBatch - 1) / perBatch);  // slots this call fills (a one-frame call fills one; the next call the next)
   if(autoFif)
   {
     size_t have = 0;
@@ -1140,13 +1157,14 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
       perBatch             = (int)std::max<size_t>(1, std::min<size_t>((size_t)perBatch, fit));
     }
   }
-  // an explicit frames_in_flight is reserved in full (half per slot) even when this call renders fewer frames, so that a
+  // an explicit frames_in_flight is reserved in full (1/n per slot) even when this call renders fewer frames, so that a
   // later, longer call does not reallocate gigabytes in the middle of a render (grow-only)
-  const int reserve = std::max(perBatch, autoFif ? 0 : (dual ? (fif + 1) / 2 : fif));
+  const int batchSlots = dual ? ctx->numSlots : 1;  // slots a multi-frame call uses
+  const int reserve    = std::max(perBatch, autoFif ? 0 : (fif + batchSlots - 1) / batchSlots);
   if((uint64_t)nLocal * (uint64_t)reserve > 0xffffffffull)
     return fail(ctx, VKRT_ERR_INVALID, "render: pixels x frames_in_flight exceeds 2^32 paths");
-  if(slotsNow == 2 || !autoFif)
-    for(int k = 0; k < (dual ? 2 : 1) && rc == VKRT_OK; k++)
+  if(slotsNow > 1 || !autoFif)
+    for(int k = 0; k < (autoFif ? slotsNow : batchSlots) && rc == VKRT_OK; k++)
       rc = ensureSlot(ctx, ctx->slots[k], (size_t)nLocal * reserve);
   if(rc != VKRT_OK) return rc;
   perBatch = std::min(perBatch, num_frames);
@@ -1156,7 +1174,7 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
   for(int done = 0; done < num_frames;)
   {
     const int batch = std::min(perBatch, num_frames - done);
-    WfSlot&   sl    = ctx->slots[dual ? (ctx->nextSlot++ & 1u) : 0u];
+    WfSlot&   sl    = ctx->slots[nSlots > 1 ? (ctx->nextSlot++ % (uint32_t)nSlots) : 0u];
     rc = ensureSlot(ctx, sl, (size_t)nLocal * perBatch);  // no-op once the slot is large enough
     if(rc == VKRT_OK && o.sort_rays)
       rc = ensureSlotSort(ctx, sl);

@@ -566,12 +566,95 @@ __global__ void __launch_bounds__(kShadeBlock, kShadeMinBlocks) shadeKernel(cons
 // like the reference's megakernel (pathtrace.glsl:193-343).  After three bounces a few percent of the paths are alive, and three
 // launches per bounce cost more in launch gaps and kernel tails than in work (round 1: an interactive frame ran at half the
 // batched rate).  Draw order, arithmetic and accumulation order are those of the wavefront kernels: images are bit-identical.
+// Lanes are refilled one by one: a lane whose path has ended takes the next queued path at once (warp-aggregated fetch from the
+// bounce's work cursor) instead of idling until the longest path of its warp is done -- under Russian roulette the remaining
+// lengths of 32 paths differ widely.  VKRT_TAIL_REFILL=0 compiles the round's first version (one path per lane and loop trip).
+#ifndef VKRT_TAIL_REFILL
+#define VKRT_TAIL_REFILL 1
+#endif
+#ifndef VKRT_TAIL_MINBLOCKS
+#define VKRT_TAIL_MINBLOCKS 4  // 128 registers, ~70 bytes of spills; 3 (162 registers, no spills) measured 1-2 % slower (profiles/README.md)
+#endif
 template <int PBR, int FM>
-__global__ void __launch_bounds__(128) tailKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
+__global__ void __launch_bounds__(128, VKRT_TAIL_MINBLOCKS) tailKernel(const __grid_constant__ SceneView sc, const __grid_constant__ Wavefront wf,
                                                   const __grid_constant__ FrameParams fp0, TraceStats* stats)
 {
   const uint32_t     count = wf.counters[wf.cbase];
   unsigned long long nClosest = 0, nShadow = 0;
+#if VKRT_TAIL_REFILL
+  uint32_t*      cursor = &wf.counters[wf.cbase + 1];  // this bounce's work cursor: zeroed by raygen, not used otherwise (no trace launch at this depth)
+  const uint32_t lane   = threadIdx.x & 31u;
+  const unsigned lt     = (1u << lane) - 1u;
+  bool           active = false, drained = false;
+  uint32_t       p = 0, raySeed = 0;
+  float3         o = f3(0.f), d = f3(0.f);
+  BounceState    b;
+  FrameParams    fp = fp0;
+  for(;;)
+  {
+    const unsigned idle = __ballot_sync(0xffffffffu, !active);
+    if(idle && !drained)
+    {
+      uint32_t base = 0;
+      if(lane == 0)
+        base = atomicAdd(cursor, (uint32_t)__popc(idle));
+      base    = __shfl_sync(0xffffffffu, base, 0);
+      drained = base + (uint32_t)__popc(idle) >= count;
+      const uint32_t i = base + (uint32_t)__popc(idle & lt);
+      if(!active && i < count)
+      {
+        p = wf.queueCur[i];
+        const float4 ro = wf.rayO[p], rd = wf.rayD[p], t4 = wf.thr[p], r4 = wf.rad[p], a4 = wf.absb[p];
+        o = f3(ro); d = f3(rd);
+        raySeed      = __float_as_uint(rd.w);
+        b.throughput = f3(t4); b.radiance = f3(r4); b.absorption = f3(a4);
+        b.seed       = __float_as_uint(t4.w);
+        fp.depth     = fp0.depth;
+        active       = true;
+      }
+    }
+    if(!__any_sync(0xffffffffu, active))
+      break;
+    if(active)
+    {
+      // one bounce of this lane's path
+      bool more = false;
+      const TailHit h = traceSingle<false>(sc, o, d, kInfinity, raySeed);
+      nClosest++;
+      if(sc.hasNonOpaque)
+        pcg(b.seed);  // the one draw of ClosestHit (see alphaDraw)
+      b.rayD = d;
+      const float4 hit = (h.tri == ~0u) ? f4(kInfinity, 0.f, 0.f, __uint_as_float(~0u)) : f4(h.t, h.u, h.v, __uint_as_float(h.tri));
+      if(bouncePhaseSurface(sc, fp, hit, b))
+      {
+        bouncePhaseLight<PBR>(sc, fp, b);
+        ShadeOut out;
+        out.wantNext = out.wantShadow = false;
+        bouncePhaseSample<PBR>(sc, fp, b, out);
+        if(out.wantShadow)
+        {
+          nShadow++;
+          const TailHit sh = traceSingle<true>(sc, out.shO, out.shD, out.shTmax, out.shSeed);
+          if(sh.tri == ~0u)
+            b.radiance = b.radiance + out.shC;  // the any-hit kernel's `rad += contribution`, same operand order
+        }
+        if(out.wantNext && fp.depth + 1 < fp0.state.maxDepth)
+        {
+          o = out.nextO; d = out.nextD; raySeed = b.seed;
+          fp.depth++;
+          more = true;
+        }
+      }
+      if(!more)
+      {
+        wf.thr[p]  = f4(b.throughput, __uint_as_float(b.seed));
+        wf.rad[p]  = f4(b.radiance, 0.f);
+        wf.absb[p] = f4(b.absorption, 0.f);
+        active     = false;
+      }
+    }
+  }
+#else
   for(uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
   {
     const uint32_t p  = wf.queueCur[i];
@@ -612,6 +695,7 @@ __global__ void __launch_bounds__(128) tailKernel(const __grid_constant__ SceneV
     wf.rad[p]  = f4(b.radiance, 0.f);
     wf.absb[p] = f4(b.absorption, 0.f);
   }
+#endif
   if(stats)
   {
 #pragma unroll
