@@ -222,6 +222,8 @@ def main():
     ap.add_argument("--frames-in-flight", type=int, default=0)
     ap.add_argument("--sort-rays", action="store_true", help="vkrt_render_opts.sort_rays: order each bounce's queue by octant + origin Morton key")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", choices=["peer", "gather"], default="peer", help="N > 1: how rank 0 gets the other ranks' pixels (see class Exchange)")
+    ap.add_argument("--no-verify-exchange", action="store_true", help="N > 1: skip comparing the exchanged image with an unsharded render on rank 0")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-hbm-record", action="store_true", help="skip the HBM-resident roofline record (instanced_10m sub-run, N=1)")
     ap.add_argument("--scene-file", default=None, help="render a glTF 2.0 file (.gltf / .glb: the real Sponza / DamagedHelmet when present) through the "
@@ -329,30 +331,88 @@ def main():
     lib_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     class Exchange:
-        """Image exchange of a sharded render: every rank packs the pixels it owns (RGBA32F, 1/N of the image) and rank 0 gathers and
-        scatters them -- the exact image of a single-GPU render, with 1/N of the bytes of a zero-padded full-image reduce."""
+        """Image exchange of a sharded render, two ways.
+        "peer" (default): the exchange is fused into the accumulate kernel -- every non-root rank maps rank 0's accumulation image
+        over CUDA IPC (vkrt_output_export / vkrt_peer_open) and its accumulate kernel stores each pixel it owns there as well, over
+        NVLink, while it runs (vkrt_output_set_mirror).  What is left is a 4-byte all-reduce between two vkrt_output_fence calls:
+        a cross-process fence, no pack / gather / unpack launches and no staging buffers.
+        "gather" (--exchange gather, or when the IPC mapping is refused): every rank packs the pixels it owns (RGBA32F, 1/N of the
+        image) and rank 0 gathers and scatters them.  Both give the exact image of a single-GPU render."""
 
         def __init__(self, w, h):
             self.n = [ctx.shard_size(TILE, r, world) for r in range(world)]
             self.cap = max(self.n)
-            self.mine = torch.zeros((self.cap, 4), dtype=torch.float32, device=dev)
-            self.all = [torch.zeros((self.cap, 4), dtype=torch.float32, device=dev) for _ in range(world)] if rank == 0 else None
             self.bytes = self.cap * 16
+            self.mode, self.peer_ptr, self.why = args.exchange, None, ""
+            if self.mode == "peer":
+                ok = 1
+                try:
+                    hs = [ctx.output_export() if rank == 0 else None]
+                except Exception as e:           # the broadcast below must still be entered by every rank
+                    hs, ok, self.why = [None], 0, str(e)
+                dist.broadcast_object_list(hs, src=0)
+                if rank != 0:
+                    try:
+                        self.peer_ptr = ctx.peer_open(hs[0])
+                        ctx.set_mirror(self.peer_ptr)
+                    except Exception as e:
+                        ok, self.why = 0, str(e)
+                t = torch.tensor([ok], dtype=torch.int32, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                if int(t.item()) == 0:
+                    self.close()
+                    self.mode = "gather"
+            self.token = torch.zeros(1, dtype=torch.float32, device=dev)
+            if self.mode == "gather":
+                self.mine = torch.zeros((self.cap, 4), dtype=torch.float32, device=dev)
+                self.all = [torch.zeros((self.cap, 4), dtype=torch.float32, device=dev) for _ in range(world)] if rank == 0 else None
+
+        def _fence(self):
+            ctx.output_fence()              # the collective waits for this rank's image operations (accumulate: its peer stores included)
+            dist.all_reduce(self.token)     # 4 bytes: every rank has got this far
+            ctx.output_fence()              # image operations enqueued from here on wait for the collective
 
         def run(self):
-            # everything on the library's image stream (torch.cuda.ExternalStream): pack -> NCCL gather -> scatter, no host sync
+            """After a render: the root's image holds every rank's pixels once this is through.  Everything is enqueued on the
+            library's image stream (torch.cuda.ExternalStream); no host synchronisation."""
             with torch.cuda.stream(lib_stream):
+                if self.mode == "peer":
+                    self._fence()
+                    return
                 ctx.pack_shard(TILE, rank, world, self.mine.data_ptr())
                 dist.gather(self.mine, self.all, dst=0)
                 if rank == 0:
                     for r in range(1, world):               # rank 0's own pixels are already in place
                         ctx.unpack_shard(TILE, r, world, self.all[r].data_ptr())
 
+        def release(self):
+            """After the root has enqueued its use of the frame (tonemap, read): the other ranks' next accumulate must not store
+            into the root's image before that use is through.  The gather path orders this on the root alone."""
+            if self.mode == "peer":
+                with torch.cuda.stream(lib_stream):
+                    self._fence()
+
+        def close(self):
+            if self.peer_ptr is not None:
+                ctx.set_mirror(None)
+                ctx.peer_close(self.peer_ptr)    # synchronises this context first
+                self.peer_ptr = None
+
+    live = {"ex": None}
+
     def measure(width, height, steps, warmup, fif):
         """One timed region at the given resolution: `warmup` untimed frames, then `steps` frames between two stream barriers of the
         library (CUDA events), plus the shard exchange when sharded.  Returns per-rank numbers."""
-        accum = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)
-        ctx.output_create(width, height, accum.data_ptr())
+        if live["ex"] is not None:           # mappings of the previous image go before rank 0 frees it
+            live["ex"].close()
+            live["ex"] = None
+            barrier()
+        if use_dist:
+            accum = None
+            ctx.output_create(width, height)     # library-owned: rank 0's can be exported to the other processes
+        else:
+            accum = torch.zeros((height, width, 4), dtype=torch.float32, device=dev)   # caller-owned buffer (a torch tensor)
+            ctx.output_create(width, height, accum.data_ptr())
         ctx.set_camera(ctx.make_camera(scene.camera["eye"], scene.camera["center"], scene.camera["up"], scene.camera["fov"], width / height,
                                        scene.camera.get("aperture", 0.0), 0 if scene.lights is None else len(scene.lights)))
         st = S.default_rtx_state(width, height, maxDepth=cfg["depth"], pbrMode=args.pbr_mode, fireflyClampThreshold=integral * 4.0)  # src/sample_example.cpp:110
@@ -361,6 +421,7 @@ def main():
             fif = max(1, min(64, (64 << 20) // max(n_local, 1), steps))
         opts = make_opts(frames_in_flight=fif, profile=0)   # no per-kernel events: the second stream and the second slot overlap
         ex = Exchange(width, height) if use_dist else None
+        live["ex"] = ex
         st.frame = 0
         ctx.render(st, warmup, opts)
         if ex:
@@ -401,11 +462,36 @@ def main():
         else:
             total_ms, total_rays = my_ms, rays
         return dict(st=st, opts=opts, fif=fif, accum=accum, ex=ex, total_ms=total_ms, total_rays=total_rays, exchange_ms=ms_exchange,
-                    exchange_bytes=(ex.bytes if ex else 0), wall_ms=wall_ms, launches=int(s.kernel_launches), clocks=sampler.summary(),
+                    exchange_bytes=(ex.bytes if ex else 0), exchange_mode=(ex.mode if ex else "none"), exchange_why=(ex.why if ex else ""), wall_ms=wall_ms, launches=int(s.kernel_launches), clocks=sampler.summary(),
                     stats=s, n_local=n_local)
 
     m = measure(W, H, args.steps, args.warmup, args.frames_in_flight)
     st, opts, accum = m["st"], m["opts"], m["accum"]
+
+    # ---- N > 1: the exchanged image on rank 0 must be, bit for bit, what one GPU renders unsharded (same frames)
+    verified = None
+    if use_dist and not args.no_verify_exchange and not args.scene_file:
+        ok = 1
+        if rank == 0:
+            got = ctx.output_read()
+            c1 = Context(device)
+            upload_scene(c1, scene, W, H, build_mode=args.build_mode)
+            c1.build_env_accel(scene.env)
+            c1.set_camera(c1.make_camera(scene.camera["eye"], scene.camera["center"], scene.camera["up"], scene.camera["fov"], W / H,
+                                         scene.camera.get("aperture", 0.0), 0 if scene.lights is None else len(scene.lights)))
+            s1 = S.default_rtx_state(W, H, maxDepth=cfg["depth"], pbrMode=args.pbr_mode, fireflyClampThreshold=integral * 4.0)
+            o1 = S.RenderOpts()
+            o1.sort_rays = opts.sort_rays
+            s1.frame = 0
+            c1.render(s1, args.warmup + args.steps, o1)
+            want = c1.output_read()
+            c1.close()
+            ok = 1 if np.array_equal(got, want) else 0
+            if not ok:
+                sys.stderr.write("exchange verification FAILED: %d of %d pixels differ\n" % (int((got != want).any(axis=-1).sum()), W * H))
+        t = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)    # also the barrier that keeps the other ranks off rank 0's image meanwhile
+        verified = bool(int(t.item()))
     s = m["stats"]
     total_ms, total_rays = m["total_ms"], m["total_rays"]
 
@@ -505,6 +591,8 @@ def main():
             if rank == 0:
                 ctx.tonemap_wait(f % nbuf)     # the copy that last used this staging slot (frame f - nbuf)
                 ctx.tonemap_async(tm, bufs[f % nbuf], f % nbuf)   # D2H: the displayed RGBA8 frame
+            if ex:
+                ex.release()                   # the other ranks may store the next frame into rank 0's image once its tonemap has read this one
 
         def drain():
             if rank == 0:
@@ -582,7 +670,6 @@ def main():
     # ---- C4 of BASELINE.json: the same scene at 3840x2160, tile-sharded over the ranks, in the same run (N > 1)
     c4 = None
     if use_dist and cfg["scene"] == "sponza" and not args.no_c4:
-        del accum
         m4 = measure(3840, 2160, min(args.steps, 32), 3, 0)
         c4 = {"workload": "sponza_4k (BASELINE.json configs[3]: 3840x2160, tile-sharded, exchange of the RGBA32F accumulation buffer)",
               "value": m4["total_rays"] / (m4["total_ms"] * 1e-3) / 1e6, "unit": "Mrays/s", "steps": min(args.steps, 32),
@@ -603,7 +690,8 @@ def main():
                                          "what": "vkrt_scene_commit: instance flattening + BVH build, outside the timed region (SURVEY 8d)"},
                            "resolution": [W, H], "max_depth": cfg["depth"], "spp_per_step": 1, "pbr_mode": args.pbr_mode,
                            "frames_in_flight": m["fif"],
-                           "sharding": f"{world} x interleaved {TILE}x{TILE} tiles, gather of owned pixels to rank 0" if use_dist else "none",
+                           "sharding": (f"{world} x interleaved {TILE}x{TILE} tiles; exchange: " + {"peer": "accumulate kernels store owned pixels into rank 0's image over NVLink (CUDA IPC mapping) + a 4-byte all-reduce as fence", "gather": "pack + NCCL gather of owned pixels to rank 0 + unpack"}[m["exchange_mode"]] + (f" (peer mapping refused: {m['exchange_why']})" if m["exchange_why"] else "")) if use_dist else "none",
+                           "exchange_verified": verified,
                            "l2": "per-step wavefront state (~170 B x %d paths) exceeds the 126 MB L2; the BVH/geometry is L2-resident by design" % (W * H),
                            "rays_counted": "ClosestHit + AnyHit calls (device counters)",
                            "vulkan": vulkan_probe()},
@@ -615,6 +703,8 @@ def main():
         if cb is not None:
             line["cpu_baseline"] = cb
         print(json.dumps(line))
+    if live["ex"] is not None:
+        live["ex"].close()
     if use_dist:
         dist.barrier()
         dist.destroy_process_group()

@@ -194,6 +194,26 @@ int vkrt_output_pack_shard(vkrt_ctx* ctx, int32_t tile_size, int32_t shard_rank,
  * the gathered buffers; the result is bit-identical to summing zero-padded full images. */
 int vkrt_output_unpack_shard(vkrt_ctx* ctx, int32_t tile_size, int32_t shard_rank, int32_t shard_count, const void* device_compact);
 
+/* ---- peer image: the exchange fused into the accumulate kernel (processes on one NVLink / NVSwitch node) --------
+ * Instead of pack -> gather -> unpack, every non-root rank's accumulate kernel ALSO stores each pixel it owns into the root's
+ * accumulation image, mapped into its address space over CUDA IPC: the shards arrive while the kernel runs, and what is left of
+ * the exchange is one small collective as a cross-process fence (vkrt_output_fence on both sides of it).  A rank's local image
+ * stays valid (the running mean is read from it), so nothing crosses the link twice.  The reference has no counterpart: it
+ * renders on one device (src/sample_example.cpp:417-426). */
+#define VKRT_IPC_HANDLE_BYTES 64
+/* root: CUDA IPC handle of the library-owned accumulation image (vkrt_output_create with device_rgba32f == NULL) */
+int vkrt_output_export(vkrt_ctx* ctx, uint8_t handle[VKRT_IPC_HANDLE_BYTES]);
+/* other ranks: map an exported image of ANOTHER process (any GPU of the node with peer access) / unmap it */
+int vkrt_peer_open(vkrt_ctx* ctx, const uint8_t handle[VKRT_IPC_HANDLE_BYTES], void** out_device_ptr);
+int vkrt_peer_close(vkrt_ctx* ctx, void* device_ptr);
+/* every pixel vkrt_render accumulates from now on is also stored to the same pixel of `device_rgba32f` (an image of this
+ * context's dimensions: a vkrt_peer_open mapping, or any device buffer); NULL switches it off */
+int vkrt_output_set_mirror(vkrt_ctx* ctx, void* device_rgba32f);
+/* Puts vkrt_stream(ctx) into the order of image operations at this point: work enqueued on that stream after the call runs after
+ * every image operation enqueued before it, and image operations enqueued after the call run after the work that stream held
+ * before it.  Bracket a collective with two calls and it becomes a cross-process barrier between accumulates and tonemaps. */
+int vkrt_output_fence(vkrt_ctx* ctx);
+
 /* ---- render: replaces Renderer::setPushContants + Renderer::run ---------- */
 
 /* Renders frames state->frame .. state->frame + num_frames - 1 (the reference calls

@@ -725,6 +725,51 @@ def test_async_tonemap_dual_slots_and_shard_exchange(vk, gpu):
     gpu.output_create(W, H)
 
 
+def test_mirror_stores_shards_into_a_second_image(vk, gpu):
+    """vkrt_output_set_mirror (the exchange fused into the accumulate kernel; across processes the target is a vkrt_peer_open
+    mapping of rank 0's image, bench.py --gpus N): two contexts render the two tile shards, the second mirrors into the first
+    one's image, and that image is, bit for bit, the unsharded render.  Also vkrt_output_fence / _export argument handling."""
+    import torch
+    from vk_raytrace_b200 import Context, structs as S
+    W, H = 200, 120
+    sc = small_sponza()
+    vk.upload_scene(gpu, sc, W, H)
+    st = S.default_rtx_state(W, H, maxDepth=5)
+    gpu.output_clear()
+    gpu.render(st, 6)
+    want = gpu.output_read()
+    other = Context(0)
+    other.precise_default = True                             # like the `gpu` fixture: the IEEE-exact shade kernel
+    try:
+        vk.upload_scene(other, sc, W, H)
+        gpu.output_clear()
+        gpu.sync()                                           # the other context's stores must not overtake the clear
+        other.set_mirror(gpu.output_device_ptr())
+        for f0, n in ((0, 4), (4, 2)):                       # two calls: the running mean continues through the mirror too
+            for rank, c in ((0, gpu), (1, other)):
+                o = S.RenderOpts()
+                o.shard_rank, o.shard_count, o.tile_size, o.frames_in_flight = rank, 2, 32, 2
+                c.render(S.default_rtx_state(W, H, maxDepth=5, frame=f0), n, o, sync=False)
+                c.output_fence()
+        other.sync()
+        gpu.sync()
+        assert np.array_equal(gpu.output_read(), want)
+        mine = other.output_read()                           # the mirroring context keeps its own shard locally
+        own = mine[..., 3] == 1
+        assert 0.3 * W * H < own.sum() < 0.7 * W * H and np.array_equal(mine[own], want[own])
+        other.set_mirror(None)
+        other.render(S.default_rtx_state(W, H, maxDepth=5, frame=6), 1)
+        assert np.array_equal(gpu.output_read(), want)       # switched off: the first image is no longer touched
+        assert len(gpu.output_export()) == 64                # library-owned image: exportable (opening it needs another process)
+        ext = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda:0")
+        gpu.output_create(W, H, ext.data_ptr())
+        with pytest.raises(Exception):
+            gpu.output_export()                              # caller-owned buffers are the caller's to export
+        gpu.output_create(W, H)
+    finally:
+        other.close()
+
+
 def test_forced_tree_width_gives_identical_hits(vk, ob, gpu):
     """VKRT_BUILD_FORCE_BVH2 / _BVH4 (what bench.py's HBM roofline record uses) select the tree per scene; results do not change."""
     sc = small_sponza()

@@ -263,6 +263,30 @@ class Context:
     def unpack_shard(self, tile, rank, count, device_ptr):
         self._ck(self.lib.vkrt_output_unpack_shard(self.h, tile, rank, count, device_ptr), "output_unpack_shard")
 
+    # ---- peer image (vkrt_output_export / vkrt_peer_open / vkrt_output_set_mirror / vkrt_output_fence) ----
+    def output_export(self):
+        """64-byte CUDA IPC handle of the library-owned accumulation image (what the root of a sharded render publishes)."""
+        h = (C.c_uint8 * 64)()
+        self._ck(self.lib.vkrt_output_export(self.h, h), "output_export")
+        return bytes(h)
+
+    def peer_open(self, handle):
+        """Maps an image another process exported; returns the device pointer (int)."""
+        h = (C.c_uint8 * 64).from_buffer_copy(bytes(handle))
+        p = C.c_void_p()
+        self._ck(self.lib.vkrt_peer_open(self.h, h, C.byref(p)), "peer_open")
+        return p.value
+
+    def peer_close(self, device_ptr):
+        self._ck(self.lib.vkrt_peer_close(self.h, device_ptr), "peer_close")
+
+    def set_mirror(self, device_ptr):
+        """Every pixel accumulated from now on is also stored to the same pixel of the image at `device_ptr` (None: off)."""
+        self._ck(self.lib.vkrt_output_set_mirror(self.h, device_ptr), "output_set_mirror")
+
+    def output_fence(self):
+        self._ck(self.lib.vkrt_output_fence(self.h), "output_fence")
+
     def tonemap_float(self, tm):
         out = np.empty((self.height, self.width, 4), dtype=np.float32)
         self._ck(self.lib.vkrt_tonemap_float(self.h, C.byref(tm), _ptr(out)), "tonemap_float")

@@ -106,6 +106,7 @@ struct vkrt_ctx
   // output image
   float4* image = nullptr;
   bool    ownsImage = false;
+  float4* mirror = nullptr;        // vkrt_output_set_mirror: a second image (a peer's) the accumulate kernel also stores to
   int     W = 0, H = 0;
   float4* dToneF = nullptr;
   uchar4* dTone8 = nullptr;
@@ -791,6 +792,7 @@ int vkrt_output_create(vkrt_ctx* ctx, uint32_t width, uint32_t height, void* dev
   syncAll(ctx);
   ctx->imagePending = false;
   for(bool& b : ctx->copyPending) b = false;
+  ctx->mirror = nullptr;  // a mirror belongs to the image it was set for
   if(ctx->ownsImage) cudaFree(ctx->image);
   cudaFree(ctx->dToneF); cudaFree(ctx->dTone8);
   for(uchar4*& b : ctx->dTone8Async) { cudaFree(b); b = nullptr; }
@@ -1030,6 +1032,61 @@ int vkrt_output_unpack_shard(vkrt_ctx* ctx, int32_t tile_size, int32_t shard_ran
   CTX_CHECK(imageEnd(ctx, ctx->stream));
   ctx->stats.kernel_launches++;
   CTX_CHECK(cudaGetLastError());
+  return VKRT_OK;
+}
+
+// ---- peer image: shards stored straight into the root's image by the accumulate kernel (include/vkrt_b200.h) ----------
+int vkrt_output_export(vkrt_ctx* ctx, uint8_t handle[VKRT_IPC_HANDLE_BYTES])
+{
+  static_assert(sizeof(cudaIpcMemHandle_t) == VKRT_IPC_HANDLE_BYTES, "IPC handle size");
+  if(!ctx || !handle) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if(!ctx->image || !ctx->ownsImage)
+    return fail(ctx, VKRT_ERR_INVALID, "output_export: needs a library-owned image (vkrt_output_create with device_rgba32f == NULL)");
+  cudaIpcMemHandle_t h;
+  CTX_CHECK(cudaIpcGetMemHandle(&h, ctx->image));
+  memcpy(handle, &h, sizeof(h));
+  return VKRT_OK;
+}
+
+int vkrt_peer_open(vkrt_ctx* ctx, const uint8_t handle[VKRT_IPC_HANDLE_BYTES], void** out_device_ptr)
+{
+  if(!ctx || !handle || !out_device_ptr) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  CTX_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *out_device_ptr = p;
+  return VKRT_OK;
+}
+
+int vkrt_peer_close(vkrt_ctx* ctx, void* device_ptr)
+{
+  if(!ctx || !device_ptr) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CTX_CHECK(syncAll(ctx));  // no accumulate kernel may still store through the mapping
+  if(ctx->mirror == (float4*)device_ptr)
+    ctx->mirror = nullptr;
+  CTX_CHECK(cudaIpcCloseMemHandle(device_ptr));
+  return VKRT_OK;
+}
+
+int vkrt_output_set_mirror(vkrt_ctx* ctx, void* device_rgba32f)
+{
+  if(!ctx) return VKRT_ERR_INVALID;
+  if(device_rgba32f && !ctx->image)
+    return fail(ctx, VKRT_ERR_INVALID, "output_set_mirror: no output image yet");
+  ctx->mirror = (float4*)device_rgba32f;  // read by the launches enqueued from now on (a kernel parameter)
+  return VKRT_OK;
+}
+
+int vkrt_output_fence(vkrt_ctx* ctx)
+{
+  if(!ctx) return VKRT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  CTX_CHECK(imageBegin(ctx, ctx->stream));
+  CTX_CHECK(imageEnd(ctx, ctx->stream));
   return VKRT_OK;
 }
 
@@ -1296,7 +1353,7 @@ int vkrt_render(vkrt_ctx* ctx, const RtxState* state, int32_t num_frames, const 
       // the running mean is order dependent (pathtrace.comp:126): batches accumulate in frame order, whichever slot they ran on
       ev(imageBegin(ctx, st));
       ScopedTimer t(ctx, timing, T_ACCUM);
-      launchAccumulate(st, wf, fp, ctx->image, ctx->numSMs, fuseFinish);
+      launchAccumulate(st, wf, fp, ctx->image, ctx->mirror, ctx->numSMs, fuseFinish);
     }
     ev(imageEnd(ctx, st));
     ctx->stats.kernel_launches++;

@@ -86,7 +86,8 @@ void launchTailPrecise(cudaStream_t s, const SceneView& scene, const Wavefront& 
 void launchTailFast(cudaStream_t s, const SceneView& scene, const Wavefront& wf, const FrameParams& fp, TraceStats* stats, int numSMs);
 void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, int numSMs);
 // fromRadiance: maxSamples == 1 -- the firefly clamp of finishSample is applied here and that launch is skipped
-void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, int numSMs, bool fromRadiance);
+// mirror: optional second image (a peer's, over NVLink) that receives the same stores
+void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, float4* mirror, int numSMs, bool fromRadiance);
 void launchShardCopy(cudaStream_t s, float4* image, const uint32_t* pixels, uint32_t n, float4* compact, bool toImage);
 struct MipView  // RGBA32F mip pyramid of the accumulation image (level 0 = the image itself)
 {

@@ -748,7 +748,7 @@ VKRT_D float3 temperature(float intensity)
 
 // ---- accumulate: pathtrace.comp:106,122-133 (running mean, frame order) ------------------------------------
 __global__ void __launch_bounds__(256) accumulateKernel(const __grid_constant__ Wavefront wf, const __grid_constant__ FrameParams fp,
-                                                        float4* __restrict__ image, bool fromRadiance)
+                                                        float4* __restrict__ image, float4* __restrict__ mirror, bool fromRadiance)
 {
   const uint32_t lp = blockIdx.x * blockDim.x + threadIdx.x;
   if(lp >= wf.numLocalPixels)
@@ -784,6 +784,8 @@ __global__ void __launch_bounds__(256) accumulateKernel(const __grid_constant__ 
       acc = pixelColor;
   }
   image[pixel] = f4(acc, 1.f);
+  if(mirror)
+    mirror[pixel] = f4(acc, 1.f);  // tile shards: the root's image, mapped from another process (vkrt_output_set_mirror)
 }
 
 // ---- tonemap: post.frag:98-147 (autoExposure off), tonemapping.glsl:24-65 -------------------------------------
@@ -981,9 +983,9 @@ void launchFinishSample(cudaStream_t s, const Wavefront& wf, const FrameParams& 
 {
   finishSampleKernel<<<(wf.numPaths + 255) / 256, 256, 0, s>>>(wf, fp);
 }
-void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, int, bool fromRadiance)
+void launchAccumulate(cudaStream_t s, const Wavefront& wf, const FrameParams& fp, float4* image, float4* mirror, int, bool fromRadiance)
 {
-  accumulateKernel<<<(wf.numLocalPixels + 255) / 256, 256, 0, s>>>(wf, fp, image, fromRadiance);
+  accumulateKernel<<<(wf.numLocalPixels + 255) / 256, 256, 0, s>>>(wf, fp, image, mirror, fromRadiance);
 }
 void launchMipDown(cudaStream_t s, const float4* src, int sw, int sh, float4* dst, int dw, int dh)
 {

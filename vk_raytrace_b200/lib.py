@@ -28,6 +28,7 @@ EXPORTS = [
     "vkrt_get_stats", "vkrt_reset_stats", "vkrt_mark", "vkrt_elapsed_ms",
     "vkrt_tonemap_async", "vkrt_tonemap_wait", "vkrt_host_alloc", "vkrt_host_free",
     "vkrt_stream", "vkrt_output_shard_size", "vkrt_output_pack_shard", "vkrt_output_unpack_shard",
+    "vkrt_output_export", "vkrt_peer_open", "vkrt_peer_close", "vkrt_output_set_mirror", "vkrt_output_fence",
 ]
 
 
@@ -82,6 +83,11 @@ def load_library():
     lib.vkrt_output_shard_size.argtypes = [vp, i32, i32, i32, C.POINTER(u32)]
     lib.vkrt_output_pack_shard.argtypes = [vp, i32, i32, i32, vp]
     lib.vkrt_output_unpack_shard.argtypes = [vp, i32, i32, i32, vp]
+    lib.vkrt_output_export.argtypes = [vp, vp]
+    lib.vkrt_peer_open.argtypes = [vp, vp, C.POINTER(vp)]
+    lib.vkrt_peer_close.argtypes = [vp, vp]
+    lib.vkrt_output_set_mirror.argtypes = [vp, vp]
+    lib.vkrt_output_fence.argtypes = [vp]
     _LIB = lib
     return lib
 
