@@ -64,23 +64,45 @@ class ClockSampler(threading.Thread):
         self.stop_flag = threading.Event()
         self.max_mhz = None
 
-    def _run_nvml(self):
-        """NVML polling every 10 ms (the timed region of the default run is ~0.1 s; nvidia-smi takes that long per call)."""
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-        self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-        bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+    _BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
+    def prepare(self):
+        """NVML handle ahead of the timed region (nvmlInit takes longer than a multi-GPU timed region lasts)."""
         try:
-            reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons
-        except AttributeError:
-            reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
-        while not self.stop_flag.is_set():
-            self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-            mask = int(reasons(h))
-            for n, b in bits.items():
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            try:
+                self._reasons = pynvml.nvmlDeviceGetCurrentClocksEventReasons
+            except AttributeError:
+                self._reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception:
+            self._h = None
+
+    def sample_now(self):
+        """One sample from the calling thread: called right after the timed work has been enqueued, while the GPU executes it (the
+        polling thread alone gets no sample out of a 5 ms region)."""
+        if getattr(self, "_h", None) is None:
+            return
+        try:
+            self.samples.append(float(self._nvml.nvmlDeviceGetClockInfo(self._h, self._nvml.NVML_CLOCK_SM)))
+            mask = int(self._reasons(self._h))
+            for n, b in self._BITS.items():
                 if mask & b:
                     self.reasons.add(n)
+        except Exception:
+            pass
+
+    def _run_nvml(self):
+        """NVML polling every 10 ms (the timed region of the default run is ~0.1 s; nvidia-smi takes that long per call)."""
+        if not hasattr(self, "_h"):
+            self.prepare()
+        if self._h is None:
+            raise RuntimeError("no NVML")
+        while not self.stop_flag.is_set():
+            self.sample_now()
             self.stop_flag.wait(0.01)
 
     def run(self):
@@ -429,6 +451,7 @@ def main():
         barrier()
         ctx.reset_stats()
         sampler = ClockSampler(device)
+        sampler.prepare()
         sampler.start()
         barrier()
         t_wall = time.time()
@@ -443,6 +466,7 @@ def main():
             ex.run()
             e1.record(lib_stream)
         ctx.mark(1)                          # timed region = render + exchange, CUDA events on the library's stream
+        sampler.sample_now()                 # the GPU is executing the timed work now
         my_ms = ctx.elapsed_ms()
         if ex:
             torch.cuda.synchronize()
