@@ -642,7 +642,7 @@ def main():
             dist.all_reduce(r, op=dist.ReduceOp.SUM)
             er = int(r.item())
         e2e = {"value": er / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 140 + 48, "d2h_bytes_per_step": W * H * 4, "steps": k,
-               "ms_per_step": dt / k * 1e3,
+               "ms_per_step": dt / k * 1e3, "gpu_launches_per_step": int(se.kernel_launches) / k,
                "what": "per step: vkrt_set_camera(host SceneCamera) + vkrt_render(1 frame%s) + vkrt_tonemap_async -> page-locked host RGBA8 on "
                        "rank 0; frame f's read-back overlaps the frames after it (ring of four staging buffers, rotating wavefront slots); wall clock over %d steps "
                        "including the final waits" % (", tile shard + gather to rank 0" if use_dist else "", k)}
