@@ -148,30 +148,33 @@ inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 :
 constexpr int kCB = 13, kP1 = 2;
 constexpr int F0298 = 2446, F0390 = 3196, F0541 = 4433, F0765 = 6270, F0899 = 7373, F1175 = 9633, F1501 = 12299, F1847 = 15137, F1961 = 16069,
               F2053 = 16819, F2562 = 20995, F3072 = 25172;
-inline int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
-inline uint8_t clamp8(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+// The butterflies run in 64-bit integers: for a valid stream every intermediate fits 32 bits (the IJG code computes in INT32 and so
+// gives the same values), for a corrupt one -- coefficients far outside the DCT's range -- nothing overflows and the result is merely garbage.
+using wide = int64_t;
+inline wide descale(wide x, int n) { return (x + ((wide)1 << (n - 1))) >> n; }
+inline uint8_t clamp8(wide v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
 
 void idct8x8(const int16_t* in, const uint16_t* q, uint8_t* out, size_t stride)
 {
-  int ws[64];
-  auto pass = [](int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7, int (&even)[4], int (&odd)[4]) {
-    int z1 = (s2 + s6) * F0541;
-    const int t2 = z1 - s6 * F1847, t3 = z1 + s2 * F0765;
-    const int t0 = (s0 + s4) * (1 << kCB), t1 = (s0 - s4) * (1 << kCB);
+  wide ws[64];
+  auto pass = [](wide s0, wide s1, wide s2, wide s3, wide s4, wide s5, wide s6, wide s7, wide (&even)[4], wide (&odd)[4]) {
+    wide z1 = (s2 + s6) * F0541;
+    const wide t2 = z1 - s6 * F1847, t3 = z1 + s2 * F0765;
+    const wide t0 = (s0 + s4) * (1 << kCB), t1 = (s0 - s4) * (1 << kCB);
     even[0] = t0 + t3; even[3] = t0 - t3; even[1] = t1 + t2; even[2] = t1 - t2;
-    int o0 = s7, o1 = s5, o2 = s3, o3 = s1;
+    wide o0 = s7, o1 = s5, o2 = s3, o3 = s1;
     z1 = o0 + o3;
-    int z2 = o1 + o2, z3 = o0 + o2, z4 = o1 + o3;
-    const int z5 = (z3 + z4) * F1175;
+    wide z2 = o1 + o2, z3 = o0 + o2, z4 = o1 + o3;
+    const wide z5 = (z3 + z4) * F1175;
     o0 *= F0298; o1 *= F2053; o2 *= F3072; o3 *= F1501;
     z1 *= -F0899; z2 *= -F2562; z3 = z3 * -F1961 + z5; z4 = z4 * -F0390 + z5;
     odd[0] = o0 + z1 + z3; odd[1] = o1 + z2 + z4; odd[2] = o2 + z2 + z3; odd[3] = o3 + z1 + z4;
   };
   for(int c = 0; c < 8; c++)
   {
-    int e[4], o[4];
-    pass(in[c] * q[c], in[8 + c] * q[8 + c], in[16 + c] * q[16 + c], in[24 + c] * q[24 + c], in[32 + c] * q[32 + c], in[40 + c] * q[40 + c],
-         in[48 + c] * q[48 + c], in[56 + c] * q[56 + c], e, o);
+    wide e[4], o[4];
+    pass((wide)in[c] * q[c], (wide)in[8 + c] * q[8 + c], (wide)in[16 + c] * q[16 + c], (wide)in[24 + c] * q[24 + c], (wide)in[32 + c] * q[32 + c],
+         (wide)in[40 + c] * q[40 + c], (wide)in[48 + c] * q[48 + c], (wide)in[56 + c] * q[56 + c], e, o);
     const int sh = kCB - kP1;
     ws[c]      = descale(e[0] + o[3], sh); ws[56 + c] = descale(e[0] - o[3], sh);
     ws[8 + c]  = descale(e[1] + o[2], sh); ws[48 + c] = descale(e[1] - o[2], sh);
@@ -180,8 +183,8 @@ void idct8x8(const int16_t* in, const uint16_t* q, uint8_t* out, size_t stride)
   }
   for(int r = 0; r < 8; r++)
   {
-    const int* w = ws + 8 * r;
-    int        e[4], o[4];
+    const wide* w = ws + 8 * r;
+    wide        e[4], o[4];
     pass(w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], e, o);
     const int sh = kCB + kP1 + 3;
     uint8_t*  p  = out + (size_t)r * stride;
