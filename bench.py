@@ -5,8 +5,9 @@ A *step* is one frame (1 sample per pixel, all bounces) of the workload image:
     python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
 N = 1: the `sponza_1080p` workload (configs[2] of BASELINE.json: Sponza stand-in, ~262k triangles,
 1920x1080, depth 8, Disney BSDF, HDR environment) -- the configuration the metric is quoted on.
-N > 1 (under torchrun): the same image, tiles dealt round-robin to the ranks (strong scaling), one NCCL
-reduce of the RGBA32F accumulation image at the end of the timed region.
+N > 1 (under torchrun): the same image, tiles dealt round-robin to the ranks (strong scaling).  Rank 0 gets the other
+ranks' pixels inside the timed region: their accumulate kernels store them into its image over NVLink (CUDA IPC peer
+mapping; class Exchange), and the run checks that image against an unsharded render (`config.exchange_verified`).
 
 Prints ONE JSON line (rank 0).  value = rays traced by all ranks (ClosestHit + AnyHit calls, device
 counters) / device time (CUDA events on the library stream, max over ranks).
