@@ -33,7 +33,7 @@ enum VkrtDebugMode {
   VKRT_DBG_RADIANCE  = 9,
   VKRT_DBG_WEIGHT    = 10,
   VKRT_DBG_RAYDIR    = 11,
-  VKRT_DBG_HEATMAP   = 12  /* per-pixel cost through temperature(): traversal steps x 50 ns stand in for clockRealtimeEXT */
+  VKRT_DBG_HEATMAP   = 12  /* per-pixel cost through temperature(): nanoseconds (%globaltimer) the kernels held the path, like clockRealtimeEXT (pathtrace.comp:108-117) */
 };
 
 /* alpha modes -- reference shaders/host_device.h:129-131 */

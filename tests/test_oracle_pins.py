@@ -233,3 +233,124 @@ def test_branch_scenes_reach_their_branch(ob, vk, kind):
         # (sum of squared differences: blurring an edge over k pixels divides it by ~k; the sum of absolute ones is conserved)
         gx = lambda im: (np.diff(im, axis=1) ** 2).sum()
         assert gx(a) < 0.6 * gx(b)
+
+
+def _np_post_chain(hdr, tm, auto):
+    """post.frag:98-147 + tonemapping.glsl:48-65 written again in float64 numpy from the GLSL semantics (mat3 constructors are
+    column-major, so `RGB2XYZ * RGB` has XYZ.y = 0.3575761 R + 0.7151522 G + 0.1191920 B -- post.frag:58; fragment centres at
+    (x + 0.5) / W; `textureLod(inImage, vec2(0.5), 20)` of a power-of-two image = the mean of all texels).  No dither."""
+    H, W = hdr.shape[:2]
+    rgb = hdr[..., :3].astype(np.float64)
+    if auto:
+        avg = rgb.reshape(-1, 3).mean(axis=0)
+        log_avg = avg @ np.array([0.2126, 0.7152, 0.0722])
+        y = 0.3575761 * rgb[..., 0] + 0.7151522 * rgb[..., 1] + 0.1191920 * rgb[..., 2]
+        Y = (tm.key / log_avg) * y
+        Yd = (Y * (1.0 + Y / (tm.Ywhite * tm.Ywhite))) / (1.0 + Y)
+        rgb = rgb / y[..., None] * Yd[..., None]
+
+    def u2(c):
+        A, B, Cc, D, E, F = 0.15, 0.50, 0.10, 0.20, 0.02, 0.30
+        return ((c * (A * c + Cc * B) + D * E) / (c * (A * c + B) + D * F)) - E / F
+
+    c = u2(rgb * tm.avgLum * 2.0) * (1.0 / u2(np.float64(11.2)))
+    c = np.power(c, 1.0 / 2.2)
+    c = np.clip(0.5 + (c - 0.5) * tm.contrast, 0.0, 1.0)
+    c = np.power(c, 1.0 / tm.brightness)
+    i = c @ np.array([0.299, 0.587, 0.114])
+    c = i[..., None] + (c - i[..., None]) * tm.saturation
+    u = ((np.arange(W) + 0.5) / W * tm.renderingRatio[0] - 0.5) * 2.0
+    v = ((np.arange(H) + 0.5) / H * tm.renderingRatio[1] - 0.5) * 2.0
+    c = c * (1.0 - (u[None, :] ** 2 + v[:, None] ** 2) * tm.vignette)[..., None]
+    return c
+
+
+@pytest.mark.parametrize("auto", [0, 1])
+def test_post_chain_against_an_independent_restatement(ob, auto):
+    """Tonemap, contrast, brightness, saturation, vignette and the global auto-exposure operator with every knob off its default."""
+    from vk_raytrace_b200 import structs as S
+    rng = np.random.default_rng(5)
+    H, W = 32, 64
+    hdr = np.ones((H, W, 4), dtype=np.float32)
+    hdr[..., :3] = (rng.random((H, W, 3)) ** 3 * 12.0 + 0.01).astype(np.float32)      # up to beyond the white point
+    o = ob.Oracle()
+    o.output_create(W, H)
+    o.output_write(hdr)
+    tm = S.default_tonemapper(brightness=1.3, contrast=1.2, saturation=0.8, vignette=0.4, avgLum=0.7, dither=0, autoExposure=auto, Ywhite=0.8, key=0.4)
+    tm.renderingRatio[0], tm.renderingRatio[1] = 1.0, 0.75
+    got = o.tonemap_float(tm)[..., :3].astype(np.float64)
+    want = _np_post_chain(hdr, tm, auto)
+    assert np.abs(got - want).max() < (2e-4 if auto else 2e-5), np.abs(got - want).max()
+    assert np.abs(want).max() > 0.5 and want.std() > 0.1
+
+
+def _np_bilinear(tex, uv, wrap):
+    """VK_FILTER_LINEAR at lod 0 written from the Vulkan texel-addressing rules in float64: unnormalised coordinate u*W - 0.5, the
+    two nearest texels weighted by its fraction; REPEAT (10497) = modulo, CLAMP_TO_EDGE (33071) = clamp, MIRRORED_REPEAT (33648).
+    RGBA8 UNORM texels = k / 255.  (Hardware rounds the weights to 8 fractional bits; the oracle and the kernels use full fp32
+    weights, DESIGN.md section 4 -- this pin is about addressing, wrap and orientation.)"""
+    H, W = tex.shape[:2]
+
+    def wrap_i(i, n):
+        if wrap == 10497:
+            return np.mod(i, n)
+        if wrap == 33648:
+            m = np.mod(i, 2 * n)
+            return np.where(m >= n, 2 * n - 1 - m, m)
+        return np.clip(i, 0, n - 1)
+
+    x, y = uv[..., 0].astype(np.float64) * W - 0.5, uv[..., 1].astype(np.float64) * H - 0.5
+    x0, y0 = np.floor(x), np.floor(y)
+    fx, fy = (x - x0)[..., None], (y - y0)[..., None]
+    x0, y0 = x0.astype(np.int64), y0.astype(np.int64)
+    t = tex.astype(np.float64) / 255.0
+    c00, c10 = t[wrap_i(y0, H), wrap_i(x0, W)], t[wrap_i(y0, H), wrap_i(x0 + 1, W)]
+    c01, c11 = t[wrap_i(y0 + 1, H), wrap_i(x0, W)], t[wrap_i(y0 + 1, H), wrap_i(x0 + 1, W)]
+    return (c00 * (1 - fx) + c10 * fx) * (1 - fy) + (c01 * (1 - fx) + c11 * fx) * fy
+
+
+@pytest.mark.parametrize("wrap", [10497, 33071, 33648])
+def test_texture_addressing_against_an_independent_restatement(ob, vk, wrap):
+    """A textured quad seen through debug views TEXCOORD and BASECOLOR (frame 0: rays through pixel centres).  The interpolated uv
+    must be what a float64 ray / plane intersection gives, and the base colour must be the sRGB -> linear (pow 2.2,
+    gltf_material.glsl:79-83) of a bilinear fetch at that uv times the factor -- for every wrap mode, with uv running past [0, 1]."""
+    from vk_raytrace_b200 import SceneDesc, TextureDesc, scenes, structs as S
+    rng = np.random.default_rng(3)
+    tex = (rng.random((8, 16, 4)) * 255).astype(np.uint8)
+    s = SceneDesc(name="tex_probe")
+    s.meshes = [scenes.quad((-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0), 0, uv_scale=2.5)]
+    s.nodes = [(np.eye(4, dtype=np.float32), 0)]
+    m = S.default_material(1)
+    m["pbrBaseColorFactor"] = (0.9, 0.8, 0.7, 1.0)
+    m["pbrBaseColorTexture"] = 0
+    s.materials = m
+    s.textures = [TextureDesc(tex, wrap_s=wrap, wrap_t=wrap)]
+    s.env = scenes.constant_environment(8, 4, 1.0)
+    s.camera = dict(eye=(0.3, 0.2, 3.0), center=(0.0, 0.0, 0.0), up=(0, 1, 0), fov=30.0)
+    W, H = 48, 40
+    o = ob.Oracle()
+    vk.upload_scene(o, s, W, H, packer=ob)
+    out = {}
+    for name, mode in (("uv", 7), ("base", 1)):
+        o.render(S.default_rtx_state(W, H, maxDepth=2, debugging_mode=mode, fireflyClampThreshold=1e9), 1)   # frame 0 overwrites the image; debug views go through the firefly clamp too (pathtrace.glsl:380-384)
+        out[name] = o.output_read()[..., :3].astype(np.float64)
+    # independent uv: pinhole camera of glm::lookAt / perspectiveRH_ZO (fov is vertical; image row 0 is the top, proj[1][1] *= -1)
+    eye = np.array(s.camera["eye"], dtype=np.float64)
+    f = -eye / np.linalg.norm(eye)
+    r = np.cross(f, np.array([0.0, 1.0, 0.0]))
+    r /= np.linalg.norm(r)
+    u = np.cross(r, f)
+    th = np.tan(np.radians(30.0) / 2)
+    px = ((np.arange(W) + 0.5) / W * 2 - 1) * th * (W / H)
+    py = -((np.arange(H) + 0.5) / H * 2 - 1) * th
+    d = f[None, None, :] + px[None, :, None] * r[None, None, :] + py[:, None, None] * u[None, None, :]
+    t = -eye[2] / d[..., 2]
+    hit = eye[None, None, :] + t[..., None] * d
+    inside = (np.abs(hit[..., 0]) < 0.98) & (np.abs(hit[..., 1]) < 0.98)
+    assert inside.sum() > 0.3 * W * H
+    uv = np.stack([(hit[..., 0] + 1) / 2 * 2.5, (hit[..., 1] + 1) / 2 * 2.5], axis=-1)     # quad(): uv (0,0) at (-1,-1), (2.5,2.5) at (1,1)
+    assert np.abs(out["uv"][..., :2] - uv)[inside].max() < 2e-5
+    assert uv[inside].max() > 2.0 and uv[inside].min() < 0.5                                # past one repeat
+    texel = _np_bilinear(tex, out["uv"][..., :2], wrap)[..., :3]
+    want = np.power(texel, 2.2) * np.array([0.9, 0.8, 0.7])
+    assert np.abs(out["base"] - want)[inside].max() < 2e-5
